@@ -1,0 +1,157 @@
+// stencil_tma.cuh -- operator family with TMA-staged planes (sm_100a: cp.async.bulk.tensor + mbarrier).
+//
+// Why: the plain-load kernel (kernels.cuh) keeps only one 16-B load per thread in flight towards DRAM, and
+// measured ~4.0 TB/s on y = A x at 512^3.  Here a dedicated producer warp streams the halo'd xy-tile of
+// every z-plane of the CTA's chunk into a shared-memory ring with 3-D tensor-map bulk copies, STAGES planes
+// ahead of the consumers, so the bytes in flight per SM are set by the ring depth and not by registers.
+//
+//   tile            64 x BY cells  (one consumer warp per row, one double2 per lane)
+//   box             72 x (BY+2) x 1 doubles, starting 4 columns left of the tile: a 32-B aligned start, the
+//                   same 18 sectors per row that the 66 wide halo'd row touches anyway; TMA zero-fills rows /
+//                   columns outside the array, those cells are masked
+//   ring            STAGES boxes, full[s] (TMA complete_tx) / empty[s] (one arrive per consumer warp) mbarriers
+//   consumers       keep k-1 / k / k+1 of their own column in registers (z-march), read y+-1 from the ring,
+//                   x+-1 by warp shuffle (edge lanes read the ring), fuse the epilogue functor, store with
+//                   128-B aligned double2 stores
+#pragma once
+
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
+#include "kernels.cuh"
+
+namespace pps {
+
+constexpr int kTmaBoxX = 72;
+constexpr int kTmaLead = 4;   // box starts kTmaLead columns left of the tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+template <int BY, int STAGES>
+struct TmaSmem {
+    static constexpr int kStageElems = kTmaBoxX * (BY + 2);
+    static constexpr int kStageBytes = kStageElems * 8;
+    static constexpr int kBytes = STAGES * kStageBytes + 2 * STAGES * 8;
+};
+
+template <int BY, int STAGES, bool PARITY, class Epi>
+__global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, Dims d, Box rg,
+                                                                   Coef cf, int zchunk, Epi epi, RedCtx red, const Ctl* ctl) {
+    if (ctl != nullptr && ctl->done) return;
+    constexpr int NACC = Epi::NACC;
+    constexpr int SX = kTmaBoxX;
+    using SM = TmaSmem<BY, STAGES>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * SM::kStageBytes);
+    uint64_t* empty = full + STAGES;
+
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int col0 = kFirstDataCol + 64 * blockIdx.x;
+    const int y0 = 1 + BY * blockIdx.y;
+    const int kchunk = 1 + blockIdx.z * zchunk;
+    const int kb = max(rg.k0, kchunk), ke = min(rg.k1, kchunk + zchunk);
+    const int nplanes = ke - kb + 2;   // planes kb-1 .. ke
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], BY);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double acc[NACC > 0 ? NACC : 1];
+#pragma unroll
+    for (int a = 0; a < (NACC > 0 ? NACC : 1); a++) acc[a] = 0.0;
+
+    if (kb < ke) {
+        if (warp == BY) {
+            // ---------------- producer: one lane streams the planes of this chunk through the ring
+            if (lane == 0) {
+                for (int p = 0; p < nplanes; p++) {
+                    const int s = p % STAGES;
+                    if (p >= STAGES) mbar_wait(&empty[s], ((p / STAGES) - 1) & 1);
+                    mbar_arrive_expect_tx(&full[s], SM::kStageBytes);
+                    tma_load_3d(ring + s * SM::kStageElems, &tmap, &full[s], col0 - kTmaLead, y0 - 1, kb - 1 + p);
+                }
+            }
+        } else {
+            // ---------------- consumers
+            const int col = col0 + 2 * lane;
+            const int j = y0 + warp;
+            const int i0 = col - kOff;
+            const bool jr = j >= rg.j0 && j < rg.j1;
+            const bool m0 = jr && i0 >= rg.i0 && i0 < rg.i1;
+            const bool m1 = jr && i0 + 1 >= rg.i0 && i0 + 1 < rg.i1;
+            const bool warp_any = __any_sync(kFullMask, m0 || m1);
+            const long long colc = col < d.pitch ? col : d.pitch - 2;
+            const long long rowoff = colc + d.pitch * min(j, d.ny);
+            const int so = (warp + 1) * SX + kTmaLead + 2 * lane;
+
+            mbar_wait(&full[0], 0);
+            double2 cm = *reinterpret_cast<const double2*>(ring + so);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[0]);
+            mbar_wait(&full[1 % STAGES], (1 / STAGES) & 1);
+            double2 cc = *reinterpret_cast<const double2*>(ring + (1 % STAGES) * SM::kStageElems + so);
+            for (int k = kb; k < ke; ++k) {
+                const int p = k - kb + 1;
+                const int s = p % STAGES, sn = (p + 1) % STAGES;
+                mbar_wait(&full[sn], ((p + 1) / STAGES) & 1);
+                const double* cur = ring + s * SM::kStageElems + so;
+                const double2 cp = *reinterpret_cast<const double2*>(ring + sn * SM::kStageElems + so);
+                if (warp_any) {
+                    const double2 ym = *reinterpret_cast<const double2*>(cur - SX);
+                    const double2 yp = *reinterpret_cast<const double2*>(cur + SX);
+                    double xl = __shfl_up_sync(kFullMask, cc.y, 1);
+                    double xr = __shfl_down_sync(kFullMask, cc.x, 1);
+                    if (lane == 0) xl = cur[-1];
+                    if (lane == 31) xr = cur[2];
+                    double2 au;
+                    au.x = laplacian<PARITY>(cf, xl, cc.x, cc.y, ym.x, yp.x, cm.x, cp.x);
+                    au.y = laplacian<PARITY>(cf, cc.x, cc.y, xr, ym.y, yp.y, cm.y, cp.y);
+                    epi(rowoff + k * d.plane, au, cc, m0, m1, acc);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                cm = cc;
+                cc = cp;
+            }
+        }
+    }
+    if (NACC > 0) grid_reduce_finish<(NACC > 0 ? NACC : 1)>(acc, red);
+}
+
+}  // namespace pps

@@ -1,0 +1,105 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures in tests/golden/ from the UNMODIFIED reference.
+
+Runs oracle/_ref/bin/ref_dump_<config> (the reference's own classes compiled against the
+threads-as-ranks MPI shim, see oracle/build_ref.py) for a list of (config, px py pz) cases
+and stores, per case, one compressed .npz with
+    history       errorFromIterationHistory_[0..iters]      (BiCGSTAB.hpp:114-117,278-281)
+    iters, norm_b, error_iteration, error_operator, tolerance
+    x             final solution, data range only, assembled to the global grid (small cases)
+    np, nranks, ds, origin, bcs, solver, precond, max_iter, cheb_max    (the configuration)
+Only runnable where /root/reference exists (the build container); the fixtures travel.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import build_ref as br  # noqa: E402
+
+# (config name, ranks, store_solution)
+CASES = [
+    ("d16", (1, 1, 1), True), ("d16", (2, 2, 2), True), ("d16", (1, 1, 2), True),
+    ("d32", (1, 1, 1), True), ("d32", (1, 1, 2), False), ("d32", (2, 1, 1), False), ("d32", (1, 2, 1), False), ("d32", (2, 2, 2), False),
+    ("d32_cheb", (1, 1, 1), True), ("d32_cheb", (2, 2, 2), False),
+    ("m24", (1, 1, 1), True), ("m24", (2, 2, 2), False), ("m24", (1, 1, 2), False),
+    ("m24_cheb", (1, 1, 1), True), ("m24_cheb", (1, 1, 2), True), ("m24_cheb", (2, 2, 1), False),
+    ("n24", (1, 1, 1), True), ("n24", (2, 1, 2), False),
+    ("cg32", (1, 1, 1), True), ("cg32", (1, 2, 2), False),
+    ("cg32_cheb", (1, 1, 1), True), ("cg32_cheb", (2, 1, 1), False),
+    ("cgm24", (1, 1, 1), True),
+    ("m32_cheb", (1, 1, 1), False), ("m32_cheb", (1, 1, 2), False),
+    ("d64", (1, 1, 1), False), ("d64", (1, 1, 2), False), ("d64", (2, 2, 2), False),
+    ("d64_t12", (1, 1, 1), False), ("d64_t12", (1, 1, 2), False), ("d64_t12", (2, 2, 2), False),
+    ("d64_cheb", (1, 1, 1), False),
+    ("default", (1, 1, 1), False), ("default", (1, 1, 2), False), ("default", (2, 1, 1), False), ("default", (2, 2, 2), False),
+]
+
+
+def read_summary(path):
+    s = {}
+    for line in open(path):
+        k, *v = line.split()
+        s[k] = v
+    return s
+
+
+def read_meta(path):
+    m = {}
+    for line in open(path):
+        k, *v = line.split()
+        m[k] = [float(t) if "." in t or "e" in t else int(t) for t in v]
+    return m
+
+
+def assemble(outdir, world, npglobal):
+    g = np.zeros((npglobal[2], npglobal[1], npglobal[0]))
+    for r in range(world):
+        m = read_meta(f"{outdir}/rank{r}.meta")
+        ng, nn, loc = m["nlocal_guards"], m["nlocal_noguards"], m["global_location"]
+        x = np.fromfile(f"{outdir}/rank{r}.x").reshape(ng[2], ng[1], ng[0])
+        o = [loc[d] * nn[d] for d in range(3)]
+        g[o[2]:o[2] + nn[2], o[1]:o[1] + nn[1], o[0]:o[0] + nn[0]] = x[1:-1, 1:-1, 1:-1]
+    return g
+
+
+def run_case(name, ranks, store_x):
+    c = br.CONFIGS[name]
+    exe = os.path.join(br.OUT, "bin", "ref_dump_" + name)
+    with tempfile.TemporaryDirectory() as td:
+        r = subprocess.run([exe, *map(str, ranks), td], check=True, capture_output=True, text=True)
+        s = read_summary(td + "/summary.txt")
+        hist = np.fromfile(td + "/history.bin")
+        world = ranks[0] * ranks[1] * ranks[2]
+        maxerr = [l for l in r.stdout.splitlines() if l.startswith("Max error local point")]
+        out = dict(
+            history=hist, iters=int(s["iters"][0]), norm_b=float(s["norm_b"][0]),
+            error_iteration=float(s["error_iteration"][0]), error_operator=float(s["error_operator"][0]),
+            tolerance=float(s["tolerance"][0]), max_iter=int(s["max_iter"][0]),
+            np=np.array(c["np"]), nranks=np.array(ranks), ds=np.array(c["ds"], dtype=float),
+            origin=np.array(c["origin"], dtype=float), bcs=np.array(c["bcs"]),
+            solver=c["solver"].split("_")[0], precond=c["solver"].split("_")[1], cheb_max=c["cheb_max"],
+            max_point_error=float(maxerr[0].split()[4]) if maxerr else np.nan,
+        )
+        if store_x:
+            out["x"] = assemble(td, world, c["np"])
+    fn = os.path.join(HERE, f"{name}_{ranks[0]}{ranks[1]}{ranks[2]}.npz")
+    np.savez_compressed(fn, **out)
+    return fn, out["iters"]
+
+
+if __name__ == "__main__":
+    br.build(sorted({c[0] for c in CASES}))
+    only = set(sys.argv[1:])
+    for name, ranks, store_x in CASES:
+        if only and name not in only:
+            continue
+        fn, iters = run_case(name, ranks, store_x)
+        print(os.path.basename(fn), "iters", iters, os.path.getsize(fn) // 1024, "KiB")

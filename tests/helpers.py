@@ -1,0 +1,87 @@
+"""Shared test plumbing: golden fixtures, oracle <-> CUDA problem hand-over."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+
+from oracle import pyoracle as po
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+
+def golden_names():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def load_golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    return {k: g[k] for k in g.files}
+
+
+def oracle_config_from_golden(g, nranks=None, max_iter=None, tolerance=None):
+    solver = po.SOLVER_CG if str(g["solver"]) == "cg" else po.SOLVER_BICGSTAB
+    precond = po.PRECOND_CHEBYSHEV if str(g["precond"]) == "cheb" else po.PRECOND_NONE
+    return po.make_config(
+        np_=[int(v) for v in g["np"]], nranks=[int(v) for v in (g["nranks"] if nranks is None else nranks)],
+        ds=[float(v) for v in g["ds"]], origin=[float(v) for v in g["origin"]], bcs=[int(v) for v in g["bcs"]],
+        solver=solver, precond=precond, tolerance=float(g["tolerance"]) if tolerance is None else tolerance,
+        max_iter=int(g["max_iter"]) if max_iter is None else max_iter, cheb_max=int(g["cheb_max"]))
+
+
+def assemble_global(fields, blocks, npglobal):
+    """per-rank guard-padded arrays -> global data-range array (k, j, i)"""
+    out = np.zeros((npglobal[2], npglobal[1], npglobal[0]))
+    for f, bi in zip(fields, blocks):
+        nn = [bi[0][d] for d in range(3)]
+        loc = [bi[1][d] for d in range(3)]
+        o = [loc[d] * nn[d] for d in range(3)]
+        out[o[2]:o[2] + nn[2], o[1]:o[1] + nn[1], o[0]:o[0] + nn[0]] = f[1:-1, 1:-1, 1:-1]
+    return out
+
+
+def oracle_global_solution(o: po.Oracle):
+    blocks = []
+    for r in range(o.world):
+        bi = o.block(r)
+        blocks.append((list(bi.nlocal), list(bi.loc)))
+    return assemble_global([o.x(r) for r in range(o.world)], blocks, list(o.cfg.np))
+
+
+# ---------------------------------------------------------------- CUDA side
+def pps_config_from_oracle(ocfg: po.OrcConfig, **over):
+    import parallelpoissonsolver_b200 as pps
+    kw = dict(
+        npglobal=list(ocfg.np), nranks=list(ocfg.nranks), ds=list(ocfg.ds), origin=list(ocfg.origin), bcs=list(ocfg.bcs),
+        solver=pps.SOLVER_CG if ocfg.solver == po.SOLVER_CG else pps.SOLVER_BICGSTAB,
+        precond=pps.PRECOND_CHEBYSHEV if ocfg.precond == po.PRECOND_CHEBYSHEV else pps.PRECOND_NONE,
+        tolerance=ocfg.tolerance, max_iter=ocfg.max_iter, cheb_max_iter=ocfg.cheb_max, cheb_epsilon=ocfg.cheb_epsilon,
+        cheb_rescale_min=ocfg.cheb_rescale_min, cheb_rescale_max=ocfg.cheb_rescale_max)
+    kw.update(over)
+    return pps.make_config(**kw)
+
+
+def hand_over_problem(o: po.Oracle, s, ranks=None):
+    """give the CUDA solver the oracle's setProblem() arrays and du/dn face values (bit-identical inputs)"""
+    for r in (ranks if ranks is not None else range(o.world)):
+        s.set_fields(r, np.ascontiguousarray(o.x(r)), np.ascontiguousarray(o.b(r)))
+        bi = o.block(r)
+        for f in range(6):
+            if bi.has_boundary[f] and o.cfg.bcs[f] == 1:
+                s.set_neumann_face(r, f, o.neumann_face(r, f))
+
+
+def pps_global_solution(s, ocfg):
+    nr = ocfg.nranks[0] * ocfg.nranks[1] * ocfg.nranks[2]
+    blocks, fields = [], []
+    for r in range(nr):
+        bi = s.block(r)
+        blocks.append((list(bi.nlocal_noguards), list(bi.global_location)))
+        fields.append(s.get_solution(r))
+    return assemble_global(fields, blocks, list(ocfg.np))
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel()))

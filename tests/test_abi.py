@@ -1,0 +1,65 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
+include/pps_b200.h declares; no compute is called (there is no GPU here and no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import parallelpoissonsolver_b200 as pps
+from parallelpoissonsolver_b200 import build as pbuild
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pps_b200.h")
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pps_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_for_sm100a():
+    lib = pbuild.build_library()
+    assert os.path.exists(lib)
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_every_declared_symbol_is_exported():
+    pbuild.build_library()
+    L = ctypes.CDLL(pps.library_path())
+    names = _declared_symbols()
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_default_config_is_the_shipped_reference_problem():
+    pbuild.build_library()
+    c = pps.default_config()
+    # inputParam.hpp:41-45, solverSetup.hpp:22-40
+    assert list(c.npglobal) == [128, 128, 256] and list(c.bcs_type) == [0, 1, 0, 1, 0, 1]
+    assert list(c.ds) == [0.1, 0.1, 0.1] and list(c.guards) == [1, 1, 1]
+    assert c.solver == pps.SOLVER_BICGSTAB and c.precond == pps.PRECOND_CHEBYSHEV
+    assert c.tolerance == 1e2 * 1e-10 and c.max_iter == 1700 and c.cheb_max_iter == 11
+    assert c.cheb_rescale_min == 500 and c.cheb_rescale_max == 1 - 1e-4 and c.cheb_epsilon == 1e-4
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    pbuild.build_library()
+    with pytest.raises(pps.PpsError) as e:
+        pps.PoissonSolver(pps.make_config((16, 16, 16)))
+    assert "no CUDA device" in str(e.value) or "CPU fallback" in str(e.value)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from parallelpoissonsolver_b200 import api
+    monkeypatch.setattr(api, "_lib", None)
+    monkeypatch.setenv("PPS_B200_LIBRARY", "/nonexistent/libpps_b200.so")
+    with pytest.raises(pps.PpsError):
+        api.load_library()

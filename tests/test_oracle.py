@@ -1,0 +1,134 @@
+"""CPU tests: the oracle restatement against the golden fixtures of the UNMODIFIED reference
+(tests/golden/, made by tests/golden/make_golden.py from oracle/_ref) and against the archived run the
+reference ships (solverPoissonMPI_CPU/run/solverScoreP.o).  Bit-exact: same iteration count, same
+residual history to the last bit, same solution on the data range."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests import helpers as H
+
+FAST_CASES = [n for n in H.golden_names()
+              if n.split("_")[0] in ("d16", "d32", "m24", "n24", "cg32", "cgm24", "m32") or n in ("d64_111", "d64_cheb_111")]
+SLOW_CASES = [n for n in H.golden_names() if n not in FAST_CASES]
+
+
+def _run_case(name):
+    g = H.load_golden(name)
+    o = po.Oracle(H.oracle_config_from_golden(g))
+    o.set_problem()
+    o.solve()
+    assert o.iters == int(g["iters"])
+    h = o.history()
+    assert h.shape == g["history"].shape
+    assert np.array_equal(h, g["history"]), "residual history differs from the reference"
+    assert o.norm_b == float(g["norm_b"])
+    assert o.error_operator == float(g["error_operator"])
+    assert o.error_iteration == float(g["error_iteration"])
+    if "x" in g:
+        assert np.array_equal(H.oracle_global_solution(o), g["x"]), "solution differs from the reference"
+    if not np.isnan(g["max_point_error"]):
+        _, m = o.check_solution()
+        # reference prints 6 significant digits (iterativeSolverBase.hpp:397)
+        assert float("%.6g" % m.max()) == float(g["max_point_error"])
+    o.close()
+
+
+@pytest.mark.parametrize("name", FAST_CASES)
+def test_oracle_matches_reference_golden(name):
+    _run_case(name)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", SLOW_CASES)
+def test_oracle_matches_reference_golden_slow(name):
+    _run_case(name)
+
+
+def test_archived_run_norm_b():
+    """solverPoissonMPI_CPU/run/solverScoreP.o:9 prints 'norm fieldB 1.10747e+07' for the shipped default
+    problem on 4x4x4 ranks; the norm does not depend on the solver, so max_iter = 0 is enough."""
+    c = po.OrcConfig()
+    po.lib().orc_default_config(c)
+    c.max_iter = 0
+    for nr in ((1, 1, 1), (4, 4, 4)):
+        c.nranks[:] = nr
+        o = po.Oracle(c)
+        o.set_problem()
+        o.solve()
+        assert "%.6g" % o.norm_b == "1.10747e+07"
+        assert o.iters == 0
+        o.close()
+
+
+def test_archived_run_geometry():
+    """solverScoreP.o:4-9: 4x4x4 ranks of 128x128x256 -> local 32 32 64, guards 34 34 66, rank 0 limits."""
+    c = po.OrcConfig()
+    po.lib().orc_default_config(c)
+    c.nranks[:] = (4, 4, 4)
+    o = po.Oracle(c)
+    b = o.block(0)
+    assert list(b.nlocal) == [32, 32, 64] and list(b.nguards) == [34, 34, 66] and b.ntot == 76296
+    assert list(b.limits_data) == [1, 33, 1, 33, 1, 65]
+    assert list(b.limits_solver) == [2, 33, 2, 33, 2, 65]
+    b63 = o.block(63)
+    assert list(b63.loc) == [3, 3, 3]
+    assert list(b63.limits_solver) == [1, 33, 1, 33, 1, 65]   # Neumann on every + face: boundary plane is solved for
+    o.close()
+
+
+def test_manufactured_solution_is_consistent():
+    """f = laplace(u) and du/dn = grad(u) (solverSetup.hpp:44-111), checked by finite differences."""
+    L = po.lib()
+    x, y, z, e = 0.37, -0.81, 1.9, 1e-4
+    lap = ((L.orc_exact_u(x + e, y, z) - 2 * L.orc_exact_u(x, y, z) + L.orc_exact_u(x - e, y, z)) +
+           (L.orc_exact_u(x, y + e, z) - 2 * L.orc_exact_u(x, y, z) + L.orc_exact_u(x, y - e, z)) +
+           (L.orc_exact_u(x, y, z + e) - 2 * L.orc_exact_u(x, y, z) + L.orc_exact_u(x, y, z - e))) / e ** 2
+    assert abs(lap - L.orc_exact_f(x, y, z)) < 1e-5
+    for d, (dx, dy, dz) in enumerate(((e, 0, 0), (0, e, 0), (0, 0, e))):
+        fd = (L.orc_exact_u(x + dx, y + dy, z + dz) - L.orc_exact_u(x - dx, y - dy, z - dz)) / (2 * e)
+        assert abs(fd - L.orc_exact_dudn(x, y, z, d)) < 1e-6
+
+
+def test_halo_exchange_moves_faces_only():
+    cfg = po.make_config((8, 6, 10), (2, 1, 2), bcs=(0, 0, 0, 0, 0, 0))
+    o = po.Oracle(cfg)
+    rng = np.random.default_rng(0)
+    fields = [rng.standard_normal(o.shape(r)) for r in range(o.world)]
+    before = [f.copy() for f in fields]
+    o.halo_exchange(fields)
+    # rank 0 (loc 0,0,0): x+ guard plane comes from rank 1's first data plane, z+ from rank 2
+    np.testing.assert_array_equal(fields[0][1:-1, 1:-1, -1], before[1][1:-1, 1:-1, 1])
+    np.testing.assert_array_equal(fields[0][-1, 1:-1, 1:-1], before[2][1, 1:-1, 1:-1])
+    # data cells never change
+    for f, b in zip(fields, before):
+        np.testing.assert_array_equal(f[1:-1, 1:-1, 1:-1], b[1:-1, 1:-1, 1:-1])
+    o.close()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(H.ROOT if hasattr(H, "ROOT") else os.path.dirname(H.HERE), "oracle", "_ref", "bin", "ref_dump_d16")),
+                    reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("ranks", [(1, 1, 1), (2, 1, 2)])
+def test_oracle_matches_reference_binary_live(ranks):
+    """run the unmodified reference here (when it was built) and compare bit for bit"""
+    root = os.path.dirname(H.HERE)
+    exe = os.path.join(root, "oracle", "_ref", "bin", "ref_dump_d16")
+    with tempfile.TemporaryDirectory() as td:
+        subprocess.run([exe, *map(str, ranks), td], check=True, capture_output=True)
+        hist = np.fromfile(td + "/history.bin")
+        cfg = po.make_config((16, 16, 16), ranks, bcs=(0, 0, 0, 0, 0, 0), tolerance=1e-8)
+        o = po.Oracle(cfg)
+        o.set_problem()
+        for r in range(o.world):
+            assert np.array_equal(np.fromfile(f"{td}/rank{r}.x0").reshape(o.shape(r)), o.x(r))
+            assert np.array_equal(np.fromfile(f"{td}/rank{r}.b0").reshape(o.shape(r)), o.b(r))
+        o.solve()
+        assert np.array_equal(o.history(), hist)
+        for r in range(o.world):
+            x = np.fromfile(f"{td}/rank{r}.x").reshape(o.shape(r))
+            assert np.array_equal(x[1:-1, 1:-1, 1:-1], o.x(r)[1:-1, 1:-1, 1:-1])
+        o.close()
