@@ -1,0 +1,353 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native Poisson hot path (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|<n>|<nx>x<ny>x<nz>]
+
+A "step" is one full solve to relative residual 1e-8 of the manufactured-solution Poisson problem
+(all-Dirichlet, unpreconditioned BiCGSTAB: BASELINE.json configs[1] at N = 1, configs[2] = 1024^3 in z-slabs
+at N > 1).  metric = MLUP/s = cells * iterations / solve seconds (whole job, max over ranks).
+  value   solve from fields already resident in HBM, timed on the device with CUDA events inside the library
+  e2e     the same solve through the C ABI from HOST buffers: pps_set_fields (H2D) + pps_solve + pps_get_solution (D2H)
+  roofline / cpu_baseline / clocks / gpu_launches: see the JSON keys below
+--impl reference times the UNMODIFIED reference CPU solver (oracle/_ref, threads-as-ranks MPI shim) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+TOL = 1e-8
+DS = 0.1
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def parse_workload(arg, n_gpus):
+    if arg == "auto":
+        n = (512, 512, 512) if n_gpus == 1 else (1024, 1024, 1024)
+    elif "x" in arg:
+        n = tuple(int(v) for v in arg.split("x"))
+    else:
+        n = (int(arg),) * 3
+    return n
+
+
+def manufactured_slab(npglobal, nranks, rank):
+    """setProblem() of the reference (iterativeSolverBase.hpp:51-55, 537-603) for one z-slab, vectorised on the host:
+    x = u_exact on the Dirichlet boundary planes, 0 inside; b = f on the data range.  Reference layout with guards."""
+    nx, ny, nzg = npglobal
+    nz = nzg // nranks
+    k0 = rank * nz
+    xs = np.arange(nx) * DS
+    ys = np.arange(ny) * DS
+    zs = (np.arange(nz) + k0) * DS
+    X = np.zeros((nz + 2, ny + 2, nx + 2))
+    B = np.zeros((nz + 2, ny + 2, nx + 2))
+    sx, cy = np.sin(xs)[None, None, :], np.cos(ys)[None, :, None]
+    yb = ys[None, :, None]
+    step = max(1, 2 ** 24 // (nx * ny))   # z-chunks bound the temporaries
+    for a in range(0, nz, step):
+        zz = zs[a:a + step][:, None, None]
+        B[1 + a:1 + a + zz.shape[0], 1:-1, 1:-1] = -sx - cy - 3 * np.sin(zz) + 2 * yb * zz + 2
+
+    def u(zz, yy, xx):
+        return np.sin(xx) + np.cos(yy) + 3 * np.sin(zz) + xx * xx * yy * zz + xx * xx + 10
+
+    X[1:-1, 1:-1, 1] = u(zs[:, None], ys[None, :], xs[0])
+    X[1:-1, 1:-1, nx] = u(zs[:, None], ys[None, :], xs[-1])
+    X[1:-1, 1, 1:-1] = u(zs[:, None], ys[0], xs[None, :])
+    X[1:-1, ny, 1:-1] = u(zs[:, None], ys[-1], xs[None, :])
+    if rank == 0:
+        X[1, 1:-1, 1:-1] = u(zs[0], ys[:, None], xs[None, :])
+    if rank == nranks - 1:
+        X[nz, 1:-1, 1:-1] = u(zs[-1], ys[:, None], xs[None, :])
+    return X, B
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md 'clocks' line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def host_rank_layout(npglobal, cores):
+    """px py pz for the threads-as-ranks reference run: z-slabs, largest power of two <= cores that divides nz"""
+    r = 1
+    while r * 2 <= min(cores, 64) and npglobal[2] % (r * 2) == 0 and npglobal[2] // (r * 2) >= 4:
+        r *= 2
+    return (1, 1, r)
+
+
+def run_reference_sample(npglobal):
+    """One bounded sample of the workload on the host cores with the unmodified reference (oracle/_ref) or,
+    when it was not built, the oracle port.  Returns dict(value MLUP/s, cores, kind, sample, seconds, iters)."""
+    cores = os.cpu_count() or 1
+    name = {(512, 512, 512): "bench512_it8", (1024, 1024, 1024): "bench1024_it2", (256, 256, 256): "bench256"}.get(tuple(npglobal))
+    exe = os.path.join(ROOT, "oracle", "_ref", "bin", "ref_solver_" + str(name))
+    cells = npglobal[0] * npglobal[1] * npglobal[2]
+    if name and os.path.exists(exe):
+        lay = host_rank_layout(npglobal, cores)
+        out = subprocess.run([exe, *map(str, lay)], capture_output=True, text=True, check=True).stdout
+        iters = int(re.search(r"finished with iter: (\d+)", out).group(1))
+        secs = float(re.search(r"SolverInFunction time: ([0-9.eE+-]+)", out).group(1))
+        return dict(value=cells * iters / secs / 1e6, unit="MLUP/s", cores=lay[0] * lay[1] * lay[2], kind="reference", seconds=secs, iters=iters,
+                    sample=f"unmodified solverPoissonMPI_CPU (-O3, threads-as-ranks mpi shim) {lay[0]}x{lay[1]}x{lay[2]} ranks, "
+                           f"{npglobal[0]}x{npglobal[1]}x{npglobal[2]} all-Dirichlet unpreconditioned BiCGSTAB, first {iters} iterations, "
+                           f"its own 'SolverInFunction time' (main.cpp:123)")
+    # fallback: the C restatement, single thread, smaller grid
+    from oracle import pyoracle as po
+    n = 128
+    cfg = po.make_config((n, n, n), (1, 1, 1), bcs=(0,) * 6, tolerance=TOL, max_iter=40)
+    o = po.Oracle(cfg)
+    o.set_problem()
+    o.solve()
+    v = n ** 3 * o.iters / o.loop_seconds / 1e6
+    res = dict(value=v, unit="MLUP/s", cores=1, kind="port", seconds=o.loop_seconds, iters=o.iters,
+               sample=f"oracle/pps_oracle.c (scalar port), {n}^3, first {o.iters} iterations (oracle/_ref not built)")
+    o.close()
+    return res
+
+
+def reference_arm(args, npglobal, rank):
+    if rank != 0:
+        return
+    vals, secs = [], []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = run_reference_sample(npglobal)
+        if i >= args.warmup:
+            vals.append(last["value"]); secs.append(last["seconds"])
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "MLUP/s (cells*iterations/solve-seconds), Poisson solve to rel-res 1e-8", "value": v, "unit": "MLUP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3,
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(npglobal, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "MLUP/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+        "e2e": {"value": v, "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(npglobal, n_gpus):
+    return {"workload": f"{npglobal[0]}x{npglobal[1]}x{npglobal[2]} fp64 Poisson, manufactured solution, all-Dirichlet, unpreconditioned BiCGSTAB "
+                        f"to rel-residual 1e-8 (BASELINE.json configs[{1 if n_gpus == 1 else 2}])",
+            "decomposition": f"1x1x{n_gpus} z-slabs", "ds": DS, "tolerance": TOL,
+            "l2": "inputs larger than L2 (1.1 GB per vector per GPU, 7 vectors streamed per iteration)"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto")
+    ap.add_argument("--max-iter", type=int, default=6000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    npglobal = parse_workload(args.workload, max(args.gpus, world))
+
+    if args.impl == "reference":
+        reference_arm(args, npglobal, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import parallelpoissonsolver_b200 as pps
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(pps.get_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().numpy().tobytes())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def rank_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def rank_sum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    cfg = pps.make_config(npglobal, nranks=(1, 1, world), ds=(DS,) * 3, bcs=(0,) * 6, solver=pps.SOLVER_BICGSTAB,
+                          precond=pps.PRECOND_NONE, tolerance=TOL, max_iter=args.max_iter, device=local_rank)
+    solver = pps.PoissonSolver(cfg, rank=rank, world_size=world, unique_id=uid)
+    my = rank if world > 1 else 0
+    X, B = manufactured_slab(npglobal, world, rank)
+    xh = torch.from_numpy(X).pin_memory()
+    bh = torch.from_numpy(B).pin_memory()
+    outh = torch.empty_like(xh).pin_memory()
+    del X, B
+    cells = npglobal[0] * npglobal[1] * npglobal[2]
+    field_bytes = xh.numel() * 8
+
+    solver.set_fields(my, xh, bh)
+    solver.save_fields()
+
+    # ---- warm-up: full solves (the first also pays module load, NCCL channel setup, tensor-map encoding)
+    for _ in range(args.warmup):
+        solver.restore_fields()
+        barrier()
+        solver.solve()
+    barrier()
+
+    # ---- timed: K solves from HBM-resident fields; device time from the library's CUDA events, max over ranks
+    DOMINANT = 3   # KernelClass KC_XR_UPDATE: 7 of the 19 vector passes of an iteration
+    solver.set_profiling(2 + DOMINANT)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    step_s, loop_s, iters_l, launches = [], [], [], 0
+    dom_ms, dom_n = 0.0, 0
+    for _ in range(args.steps):
+        solver.restore_fields()
+        barrier()
+        solver.solve()
+        barrier()
+        step_s.append(rank_max(solver.solver_seconds))
+        loop_s.append(rank_max(solver.loop_seconds))
+        iters_l.append(solver.iterations)
+        launches += solver.launch_count
+        for k in solver.kernel_stats():
+            if k["id"] == DOMINANT:
+                dom_ms += k["avg_ms"] * k["launches"]; dom_n += k["launches"]
+    clocks = sampler.stop() if rank == 0 else None
+    solver.set_profiling(0)
+    launches = int(rank_sum(launches))
+
+    # ---- end to end through the C ABI with host buffers (pinned): H2D of x and b, solve, D2H of x
+    e2e_s = []
+    for _ in range(max(1, min(args.steps, 3))):
+        barrier()
+        t0 = time.perf_counter()
+        solver.set_fields(my, xh, bh)
+        solver.solve()
+        solver.get_solution(my, outh)
+        torch.cuda.synchronize()
+        e2e_s.append(rank_max(time.perf_counter() - t0))
+    e2e_iters = solver.iterations
+    err_true = solver.error_operator
+
+    total_iters = float(np.sum(iters_l))
+    total_s = float(np.sum(step_s))
+    value = cells * total_iters / total_s / 1e6
+    peak, peak_src = measured_peak()
+    slab_cells = cells / world
+    dom_avg_ms = dom_ms / max(1, dom_n)
+    achieved = 7 * 8 * slab_cells / dom_avg_ms / 1e6 if dom_avg_ms > 0 else None
+    iter_gbs = 136 * slab_cells * total_iters / float(np.sum(loop_s)) / 1e9
+
+    if rank == 0:
+        line = {
+            "metric": "MLUP/s (cells*iterations/solve-seconds), Poisson solve to rel-res 1e-8", "value": value, "unit": "MLUP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(npglobal, world),
+            "iterations": iters_l, "solve_seconds": step_s, "true_residual": err_true,
+            "e2e": {"value": cells * e2e_iters / float(np.mean(e2e_s)) / 1e6, "unit": "MLUP/s", "h2d_bytes_per_step": 2 * field_bytes * world,
+                    "d2h_bytes_per_step": field_bytes * world, "seconds_per_step": float(np.mean(e2e_s)),
+                    "path": "pps_set_fields + pps_solve + pps_get_solution from pinned host buffers"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "xr_update (x+=alpha*p+omega*s; r=s-omega*t; r0.r; r.r), 7 vector passes = 56 B/cell",
+                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": achieved / peak if achieved else None, "traffic": None, "launches_timed": dom_n, "avg_ms": dom_avg_ms},
+            "roofline_iteration": {"bound": "hbm", "what": "whole BiCGSTAB iteration, 136 algorithmic B/cell (17 passes; 19 are moved)",
+                                   "achieved": iter_gbs, "peak": peak, "unit": "GB/s", "frac": iter_gbs / peak},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cb = run_reference_sample(npglobal)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -148,7 +148,8 @@ int pps_apply_preconditioner(pps_handle* h, int rank, const double* b_host, doub
 /* device-resident timing of `reps` operator applies on block 0's work vectors; returns average ms */
 int pps_bench_operator(pps_handle* h, int reps, int with_dot, double* avg_ms);
 /* average device time (ms) per launch of kernel class `which` during the last pps_solve, measured with
- * CUDA events on the launching stream when profiling is enabled by pps_set_profiling(h, 1) */
+ * CUDA events on the launching stream when profiling is enabled: pps_set_profiling(h, 1) brackets every kernel
+ * class, pps_set_profiling(h, 2 + c) only class c, 0 switches it off */
 int pps_set_profiling(pps_handle* h, int enabled);
 int pps_get_kernel_stats(const pps_handle* h, int which, double* avg_ms, long long* launches, const char** name);
 long long pps_get_launch_count(const pps_handle* h);          /* kernels launched by the last pps_solve */

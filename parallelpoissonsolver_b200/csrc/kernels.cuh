@@ -245,7 +245,11 @@ __global__ void __launch_bounds__(32 * BY) stencil_kernel(const double* __restri
             double2 au;
             au.x = laplacian<PARITY>(cf, xl, cc.x, cc.y, ym.x, yp.x, cm.x, cp.x);
             au.y = laplacian<PARITY>(cf, cc.x, cc.y, xr, ym.y, yp.y, cm.y, cp.y);
-            epi(m.rowoff + k * d.plane, au, cc, m.m0, m.m1, acc);
+            const long long idx = m.rowoff + k * d.plane;
+            double2 ax[Epi::NAUX > 0 ? Epi::NAUX : 1];
+#pragma unroll
+            for (int a = 0; a < Epi::NAUX; a++) ax[a] = ldg2(epi.aux(a) + idx);
+            epi(idx, au, cc, ax, m.m0, m.m1, acc);
             cm = cc;
             cc = cp;
         }
@@ -253,82 +257,107 @@ __global__ void __launch_bounds__(32 * BY) stencil_kernel(const double* __restri
     if (NACC > 0) grid_reduce_finish<(NACC > 0 ? NACC : 1)>(acc, red);
 }
 
+// Epilogue functors.  NACC = fused reductions, NAUX = extra input streams read at the same cell (aux(i) names
+// them: the plain-load kernel fetches them with ldg, the TMA kernel stages them through its ring).
+// operator()(idx, Au, u, ax, m0, m1, acc): idx = element offset of the thread's first cell, ax[i] = aux values.
+
 // out = A u                                                      (BiCGSTAB.hpp:189-199 loop nest)
 struct EpiStore {
-    static constexpr int NACC = 0;
+    static constexpr int NACC = 0, NAUX = 0;
     double* out;
-    __device__ __forceinline__ void operator()(long long idx, double2 au, double2, bool m0, bool m1, double*) const {
+    __host__ __device__ __forceinline__ const double* aux(int) const { return nullptr; }
+    __device__ __forceinline__ void operator()(long long idx, double2 au, double2, const double2*, bool m0, bool m1, double*) const {
         st2(out + idx, au, m0, m1);
     }
 };
 // v = A p ; acc0 += w.v                                           (BiCGSTAB.hpp:142-155)
 struct EpiStoreDot {
-    static constexpr int NACC = 1;
+    static constexpr int NACC = 1, NAUX = 1;
     double* out;
     const double* w;
-    __device__ __forceinline__ void operator()(long long idx, double2 au, double2, bool m0, bool m1, double* acc) const {
+    __host__ __device__ __forceinline__ const double* aux(int) const { return w; }
+    __device__ __forceinline__ void operator()(long long idx, double2 au, double2, const double2* ax, bool m0, bool m1, double* acc) const {
         st2(out + idx, au, m0, m1);
-        const double2 wv = ldg2(w + idx);
-        acc[0] += (m0 ? wv.x * au.x : 0.0) + (m1 ? wv.y * au.y : 0.0);
+        acc[0] += (m0 ? ax[0].x * au.x : 0.0) + (m1 ? ax[0].y * au.y : 0.0);
     }
 };
-// t = A s ; acc0 += w.t ; acc1 += t.t   (w = r after r -= alpha v; with no preconditioner w is the operand itself)
-//                                                                  (BiCGSTAB.hpp:189-214)
+// t = A z ; acc0 += r.t ; acc1 += t.t                              (BiCGSTAB.hpp:189-214)
 struct EpiStoreDot2 {
-    static constexpr int NACC = 2;
+    static constexpr int NACC = 2, NAUX = 1;
     double* out;
-    const double* w;   // nullptr: w = u (the operand)
-    __device__ __forceinline__ void operator()(long long idx, double2 au, double2 u, bool m0, bool m1, double* acc) const {
+    const double* w;
+    __host__ __device__ __forceinline__ const double* aux(int) const { return w; }
+    __device__ __forceinline__ void operator()(long long idx, double2 au, double2, const double2* ax, bool m0, bool m1, double* acc) const {
         st2(out + idx, au, m0, m1);
-        double2 wv = u;
-        if (w != nullptr) wv = ldg2(w + idx);
-        acc[0] += (m0 ? wv.x * au.x : 0.0) + (m1 ? wv.y * au.y : 0.0);
+        acc[0] += (m0 ? ax[0].x * au.x : 0.0) + (m1 ? ax[0].y * au.y : 0.0);
+        acc[1] += (m0 ? au.x * au.x : 0.0) + (m1 ? au.y * au.y : 0.0);
+    }
+};
+// same without a preconditioner: z is r itself, so the operand doubles as the dot-product partner
+struct EpiStoreDot2Self {
+    static constexpr int NACC = 2, NAUX = 0;
+    double* out;
+    __host__ __device__ __forceinline__ const double* aux(int) const { return nullptr; }
+    __device__ __forceinline__ void operator()(long long idx, double2 au, double2 u, const double2*, bool m0, bool m1, double* acc) const {
+        st2(out + idx, au, m0, m1);
+        acc[0] += (m0 ? u.x * au.x : 0.0) + (m1 ? u.y * au.y : 0.0);
         acc[1] += (m0 ? au.x * au.x : 0.0) + (m1 ? au.y * au.y : 0.0);
     }
 };
 // r = b - A x ; acc0 += r.r                                       (iterativeSolverBase.hpp:257-268)
 template <bool PARITY>
 struct EpiResidual {
-    static constexpr int NACC = 1;
+    static constexpr int NACC = 1, NAUX = 1;
     double* r;
     const double* b;
-    __device__ __forceinline__ void operator()(long long idx, double2 au, double2, bool m0, bool m1, double* acc) const {
-        const double2 bv = ldg2(b + idx);
+    __host__ __device__ __forceinline__ const double* aux(int) const { return b; }
+    __device__ __forceinline__ void operator()(long long idx, double2 au, double2, const double2* ax, bool m0, bool m1, double* acc) const {
         double2 rv;
-        rv.x = PARITY ? __dsub_rn(bv.x, au.x) : bv.x - au.x;
-        rv.y = PARITY ? __dsub_rn(bv.y, au.y) : bv.y - au.y;
+        rv.x = PARITY ? __dsub_rn(ax[0].x, au.x) : ax[0].x - au.x;
+        rv.y = PARITY ? __dsub_rn(ax[0].y, au.y) : ax[0].y - au.y;
         st2(r + idx, rv, m0, m1);
         acc[0] += (m0 ? rv.x * rv.x : 0.0) + (m1 ? rv.y * rv.y : 0.0);
     }
 };
 // Ap = A p ; acc0 += r.z ; acc1 += p.Ap                           (baseCG.hpp:126-140)
 struct EpiCgApply {
-    static constexpr int NACC = 2;
+    static constexpr int NACC = 2, NAUX = 2;
     double* out;
     const double* r;
     const double* z;
-    __device__ __forceinline__ void operator()(long long idx, double2 au, double2 u, bool m0, bool m1, double* acc) const {
+    __host__ __device__ __forceinline__ const double* aux(int i) const { return i == 0 ? r : z; }
+    __device__ __forceinline__ void operator()(long long idx, double2 au, double2 u, const double2* ax, bool m0, bool m1, double* acc) const {
         st2(out + idx, au, m0, m1);
-        const double2 rv = ldg2(r + idx);
-        double2 zv = rv;
-        if (z != r) zv = ldg2(z + idx);
-        acc[0] += (m0 ? rv.x * zv.x : 0.0) + (m1 ? rv.y * zv.y : 0.0);
+        acc[0] += (m0 ? ax[0].x * ax[1].x : 0.0) + (m1 ? ax[0].y * ax[1].y : 0.0);
+        acc[1] += (m0 ? u.x * au.x : 0.0) + (m1 ? u.y * au.y : 0.0);
+    }
+};
+// same without a preconditioner (z is r): acc0 += r.r
+struct EpiCgApplySelf {
+    static constexpr int NACC = 2, NAUX = 1;
+    double* out;
+    const double* r;
+    __host__ __device__ __forceinline__ const double* aux(int) const { return r; }
+    __device__ __forceinline__ void operator()(long long idx, double2 au, double2 u, const double2* ax, bool m0, bool m1, double* acc) const {
+        st2(out + idx, au, m0, m1);
+        acc[0] += (m0 ? ax[0].x * ax[0].x : 0.0) + (m1 ? ax[0].y * ax[0].y : 0.0);
         acc[1] += (m0 ? u.x * au.x : 0.0) + (m1 ? u.y * au.y : 0.0);
     }
 };
 // Chebyshev start: Z = B/theta ; Y = (2 rho1/delta) (2 B + A B/theta)       (chebyshevIteration.hpp:79-90)
-// dstY may be the final output with the sign flipped (chebyshevMax == 3 -> X = -y1)
+// Y may be the final output with the sign flipped (chebyshevMax == 3 -> X = -y1)
 template <bool PARITY>
 struct EpiChebFirst {
-    static constexpr int NACC = 0;
+    static constexpr int NACC = 0, NAUX = 0;
     double* Z;
     double* Y;
     double theta, inv_theta, c1, ysign;
+    __host__ __device__ __forceinline__ const double* aux(int) const { return nullptr; }
     __device__ __forceinline__ double y(double b, double ab) const {
         if (PARITY) return __dmul_rn(c1, __dadd_rn(__dmul_rn(2.0, b), __ddiv_rn(ab, theta)));
         return c1 * fma(ab, inv_theta, 2.0 * b);
     }
-    __device__ __forceinline__ void operator()(long long idx, double2 au, double2 u, bool m0, bool m1, double*) const {
+    __device__ __forceinline__ void operator()(long long idx, double2 au, double2 u, const double2*, bool m0, bool m1, double*) const {
         double2 zv, yv;
         zv.x = PARITY ? __ddiv_rn(u.x, theta) : u.x * inv_theta;
         zv.y = PARITY ? __ddiv_rn(u.y, theta) : u.y * inv_theta;
@@ -342,23 +371,22 @@ struct EpiChebFirst {
 // wsign = -1 folds the final X = -W (:118-128) into the last live sweep
 template <bool PARITY>
 struct EpiChebStep {
-    static constexpr int NACC = 0;
+    static constexpr int NACC = 0, NAUX = 2;
     double* W;
     const double* B;
     const double* Z;
     double rho, rho_old, two_sigma, two_over_delta, wsign;
+    __host__ __device__ __forceinline__ const double* aux(int i) const { return i == 0 ? B : Z; }
     __device__ __forceinline__ double w(double y, double ay, double b, double z) const {
         if (PARITY)
             return __dmul_rn(rho, __dsub_rn(__dadd_rn(__dmul_rn(two_sigma, y), __dmul_rn(two_over_delta, __dadd_rn(b, ay))),
                                             __dmul_rn(rho_old, z)));
         return rho * fma(-rho_old, z, fma(two_sigma, y, two_over_delta * (b + ay)));
     }
-    __device__ __forceinline__ void operator()(long long idx, double2 au, double2 u, bool m0, bool m1, double*) const {
-        const double2 bv = ldg2(B + idx);
-        const double2 zv = ldg2(Z + idx);
+    __device__ __forceinline__ void operator()(long long idx, double2 au, double2 u, const double2* ax, bool m0, bool m1, double*) const {
         double2 wv;
-        wv.x = wsign * w(u.x, au.x, bv.x, zv.x);
-        wv.y = wsign * w(u.y, au.y, bv.y, zv.y);
+        wv.x = wsign * w(u.x, au.x, ax[0].x, ax[1].x);
+        wv.y = wsign * w(u.y, au.y, ax[0].y, ax[1].y);
         st2(W + idx, wv, m0, m1);
     }
 };

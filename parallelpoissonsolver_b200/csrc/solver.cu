@@ -92,7 +92,7 @@ struct pps_handle {
     int by = 8;                 // tile rows of the plain-load kernels
     int stencil_impl = 1;       // 0 plain loads, 1 TMA ring (stencil_tma.cuh)
     int by_tma = 8;             // tile rows of the TMA operator kernels (8 or 16)
-    std::map<std::pair<const void*, int>, CUtensorMap> tmaps;
+    std::map<std::pair<const void*, int>, CUtensorMap> tmaps;   // key: (field, rows) main box; (field, -rows) aux box
     int zchunk_stencil = 0, zchunk_point = 0;   // 0 = heuristic
     int lag = 3;
     std::vector<Block> blocks;
@@ -114,6 +114,7 @@ struct pps_handle {
     double err_iter = -1, err_op = -1, norm_b = 1, solver_seconds = 0, loop_seconds = 0;
     long long launch_count = 0;
     bool profiling = false;
+    int profile_only = -1;      // >= 0: only this kernel class is bracketed with events
     KernelStat stats[KC_COUNT];
     std::vector<cudaEvent_t> event_pool;
     size_t event_next = 0;
@@ -162,8 +163,10 @@ struct LaunchScope {
     pps_handle* h;
     int kc;
     cudaEvent_t e0 = nullptr;
+    bool on;
     LaunchScope(pps_handle* h_, int kc_) : h(h_), kc(kc_) {
-        if (h->profiling) {
+        on = h->profiling && (h->profile_only < 0 || h->profile_only == kc);
+        if (on) {
             e0 = pool_event(h);
             cudaEventRecord(e0, h->stream);
         }
@@ -173,7 +176,7 @@ struct LaunchScope {
         h->stats[kc].launches += n;
     }
     ~LaunchScope() {
-        if (h->profiling) {
+        if (on) {
             cudaEvent_t e1 = pool_event(h);
             cudaEventRecord(e1, h->stream);
             h->stats[kc].pending.emplace_back(e0, e1);
@@ -267,15 +270,15 @@ static EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-static const CUtensorMap& tensor_map(pps_handle* h, const Block& b, const double* field, int by) {
-    auto key = std::make_pair(static_cast<const void*>(field), by);
+static const CUtensorMap& tensor_map(pps_handle* h, const Block& b, const double* field, int by, bool aux) {
+    auto key = std::make_pair(static_cast<const void*>(field), aux ? -by : by);
     auto it = h->tmaps.find(key);
     if (it != h->tmaps.end()) return it->second;
     CUtensorMap m;
     const Dims& d = b.g.dims;
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(d.pitch), static_cast<cuuint64_t>(d.ny + 2), static_cast<cuuint64_t>(d.nz + 2)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(d.pitch) * 8, static_cast<cuuint64_t>(d.plane) * 8};
-    cuuint32_t box[3] = {static_cast<cuuint32_t>(kTmaBoxX), static_cast<cuuint32_t>(by + 2), 1};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(aux ? 64 : kTmaBoxX), static_cast<cuuint32_t>(aux ? by : by + 2), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(field), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -285,16 +288,19 @@ static const CUtensorMap& tensor_map(pps_handle* h, const Block& b, const double
 }
 
 template <int BY, int STAGES, bool PAR, class Epi>
-static void launch_tma_inst(pps_handle* h, const CUtensorMap& tm, const Block& b, const Box& box, const Epi& epi,
+static void launch_tma_inst(pps_handle* h, const Block& b, const double* u, const Box& box, const Epi& epi,
                             const RedCtx& red, const Tiling& t, const Ctl* ctl) {
     auto kern = stencil_tma_kernel<BY, STAGES, PAR, Epi>;
     static bool attr_set = false;
-    constexpr int smem = TmaSmem<BY, STAGES>::kBytes;
+    constexpr int smem = TmaSmem<BY, STAGES, Epi::NAUX>::kBytes;
     if (!attr_set) {
         PPS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    kern<<<t.grid, t.block, smem, h->stream>>>(tm, b.g.dims, box, h->coef, t.zchunk, epi, red, ctl);
+    const CUtensorMap& tm = tensor_map(h, b, u, BY, false);
+    const CUtensorMap& a0 = Epi::NAUX > 0 ? tensor_map(h, b, epi.aux(0), BY, true) : tm;
+    const CUtensorMap& a1 = Epi::NAUX > 1 ? tensor_map(h, b, epi.aux(1), BY, true) : tm;
+    kern<<<t.grid, t.block, smem, h->stream>>>(tm, a0, a1, b.g.dims, box, h->coef, t.zchunk, epi, red, ctl);
 }
 
 template <class Epi>
@@ -303,13 +309,12 @@ static void launch_stencil(pps_handle* h, int kc, const Block& b, const double* 
     LaunchScope ls(h, kc);
     const Ctl* ctl = check_done ? h->ctl : nullptr;
     if (h->stencil_impl == 1) {
-        const CUtensorMap& tm = tensor_map(h, b, u, h->by_tma);
         if (h->by_tma == 16) {
-            if (h->parity) launch_tma_inst<16, 4, true>(h, tm, b, box, epi, red, t, ctl);
-            else           launch_tma_inst<16, 4, false>(h, tm, b, box, epi, red, t, ctl);
+            if (h->parity) launch_tma_inst<16, 4, true>(h, b, u, box, epi, red, t, ctl);
+            else           launch_tma_inst<16, 4, false>(h, b, u, box, epi, red, t, ctl);
         } else {
-            if (h->parity) launch_tma_inst<8, 6, true>(h, tm, b, box, epi, red, t, ctl);
-            else           launch_tma_inst<8, 6, false>(h, tm, b, box, epi, red, t, ctl);
+            if (h->parity) launch_tma_inst<8, 6, true>(h, b, u, box, epi, red, t, ctl);
+            else           launch_tma_inst<8, 6, false>(h, b, u, box, epi, red, t, ctl);
         }
     } else {
 #define PPS_LAUNCH_ST(BYV, PAR) \
@@ -686,7 +691,8 @@ static void bicgstab_iteration(pps_handle* h) {
             const Box box = b.g.solver_box();
             const Tiling t = make_tiling(h, b.g, box, true);
             RedCtx red = make_red(h, 2, total, off, OP_BICG_OMEGA);
-            launch_stencil(h, KC_APPLY_DOT2, b, b.z, box, EpiStoreDot2{b.t, b.z == b.r ? nullptr : b.r}, red, t, true);   // :189-214
+            if (b.z == b.r) launch_stencil(h, KC_APPLY_DOT2, b, b.z, box, EpiStoreDot2Self{b.t}, red, t, true);   // :189-214
+            else            launch_stencil(h, KC_APPLY_DOT2, b, b.z, box, EpiStoreDot2{b.t, b.r}, red, t, true);
             off += t.ctas();
         }
         finish_reduction(h, 2, OP_BICG_OMEGA, false);                         // :216-225
@@ -723,7 +729,8 @@ static void cg_iteration(pps_handle* h) {
             const Box box = b.g.solver_box();
             const Tiling t = make_tiling(h, b.g, box, true);
             RedCtx red = make_red(h, 2, total, off, OP_CG_ALPHA);
-            launch_stencil(h, KC_CG_APPLY, b, b.p, box, EpiCgApply{b.v, b.r, b.z}, red, t, true);   // :126-140
+            if (b.z == b.r) launch_stencil(h, KC_CG_APPLY, b, b.p, box, EpiCgApplySelf{b.v, b.r}, red, t, true);   // :126-140
+            else            launch_stencil(h, KC_CG_APPLY, b, b.p, box, EpiCgApply{b.v, b.r, b.z}, red, t, true);
             off += t.ctas();
         }
         finish_reduction(h, 2, OP_CG_ALPHA, false);
@@ -1231,7 +1238,9 @@ int pps_bench_operator(pps_handle* h, int reps, int with_dot, double* avg_ms) {
 }
 
 int pps_set_profiling(pps_handle* h, int enabled) {
+    // 0 off, 1 every kernel class, 2 + c only kernel class c (two event records per launch of that class)
     h->profiling = enabled != 0;
+    h->profile_only = enabled >= 2 ? enabled - 2 : -1;
     return 0;
 }
 

@@ -57,20 +57,26 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
-template <int BY, int STAGES>
+template <int BY, int STAGES, int NAUX>
 struct TmaSmem {
-    static constexpr int kStageElems = kTmaBoxX * (BY + 2);
+    static constexpr int kMainElems = kTmaBoxX * (BY + 2);
+    static constexpr int kAuxElems = 64 * BY;                      // aux streams need no halo
+    static constexpr int kStageElems = kMainElems + NAUX * kAuxElems;
+    static constexpr int kMainBytes = kMainElems * 8;
     static constexpr int kStageBytes = kStageElems * 8;
     static constexpr int kBytes = STAGES * kStageBytes + 2 * STAGES * 8;
 };
 
 template <int BY, int STAGES, bool PARITY, class Epi>
-__global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, Dims d, Box rg,
+__global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                   const __grid_constant__ CUtensorMap tmap_a0,
+                                                                   const __grid_constant__ CUtensorMap tmap_a1, Dims d, Box rg,
                                                                    Coef cf, int zchunk, Epi epi, RedCtx red, const Ctl* ctl) {
     if (ctl != nullptr && ctl->done) return;
     constexpr int NACC = Epi::NACC;
+    constexpr int NAUX = Epi::NAUX;
     constexpr int SX = kTmaBoxX;
-    using SM = TmaSmem<BY, STAGES>;
+    using SM = TmaSmem<BY, STAGES, NAUX>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * SM::kStageBytes);
@@ -103,8 +109,15 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid
                 for (int p = 0; p < nplanes; p++) {
                     const int s = p % STAGES;
                     if (p >= STAGES) mbar_wait(&empty[s], ((p / STAGES) - 1) & 1);
-                    mbar_arrive_expect_tx(&full[s], SM::kStageBytes);
-                    tma_load_3d(ring + s * SM::kStageElems, &tmap, &full[s], col0 - kTmaLead, y0 - 1, kb - 1 + p);
+                    double* dst = ring + s * SM::kStageElems;
+                    // aux streams are only read where the operator is evaluated: planes kb .. ke-1
+                    const bool with_aux = NAUX > 0 && p >= 1 && p <= nplanes - 2;
+                    mbar_arrive_expect_tx(&full[s], with_aux ? SM::kStageBytes : SM::kMainBytes);
+                    tma_load_3d(dst, &tmap, &full[s], col0 - kTmaLead, y0 - 1, kb - 1 + p);
+                    if (with_aux) {
+                        if (NAUX > 0) tma_load_3d(dst + SM::kMainElems, &tmap_a0, &full[s], col0, y0, kb - 1 + p);
+                        if (NAUX > 1) tma_load_3d(dst + SM::kMainElems + SM::kAuxElems, &tmap_a1, &full[s], col0, y0, kb - 1 + p);
+                    }
                 }
             }
         } else {
@@ -119,6 +132,7 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid
             const long long colc = col < d.pitch ? col : d.pitch - 2;
             const long long rowoff = colc + d.pitch * min(j, d.ny);
             const int so = (warp + 1) * SX + kTmaLead + 2 * lane;
+            const int sa = SM::kMainElems + warp * 64 + 2 * lane;
 
             mbar_wait(&full[0], 0);
             double2 cm = *reinterpret_cast<const double2*>(ring + so);
@@ -130,11 +144,15 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid
                 const int p = k - kb + 1;
                 const int s = p % STAGES, sn = (p + 1) % STAGES;
                 mbar_wait(&full[sn], ((p + 1) / STAGES) & 1);
-                const double* cur = ring + s * SM::kStageElems + so;
+                const double* stg = ring + s * SM::kStageElems;
+                const double* cur = stg + so;
                 const double2 cp = *reinterpret_cast<const double2*>(ring + sn * SM::kStageElems + so);
                 if (warp_any) {
                     const double2 ym = *reinterpret_cast<const double2*>(cur - SX);
                     const double2 yp = *reinterpret_cast<const double2*>(cur + SX);
+                    double2 ax[NAUX > 0 ? NAUX : 1];
+#pragma unroll
+                    for (int a = 0; a < NAUX; a++) ax[a] = *reinterpret_cast<const double2*>(stg + sa + a * SM::kAuxElems);
                     double xl = __shfl_up_sync(kFullMask, cc.y, 1);
                     double xr = __shfl_down_sync(kFullMask, cc.x, 1);
                     if (lane == 0) xl = cur[-1];
@@ -142,7 +160,7 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid
                     double2 au;
                     au.x = laplacian<PARITY>(cf, xl, cc.x, cc.y, ym.x, yp.x, cm.x, cp.x);
                     au.y = laplacian<PARITY>(cf, cc.x, cc.y, xr, ym.y, yp.y, cm.y, cp.y);
-                    epi(rowoff + k * d.plane, au, cc, m0, m1, acc);
+                    epi(rowoff + k * d.plane, au, cc, ax, m0, m1, acc);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
