@@ -154,6 +154,12 @@ int pps_set_profiling(pps_handle* h, int enabled);
 int pps_get_kernel_stats(const pps_handle* h, int which, double* avg_ms, long long* launches, const char** name);
 long long pps_get_launch_count(const pps_handle* h);          /* kernels launched by the last pps_solve */
 int pps_synchronize(pps_handle* h);
+/* lower the iteration cap of later solves (<= the max_iter the handle was created with) */
+int pps_set_max_iterations(pps_handle* h, int max_iter);
+/* out[r*n .. r*n+n) = in of rank r, on every rank: the error gather of checkSolutionLocalGlobal
+ * (iterativeSolverBase.hpp:320-373, point-to-point to rank 0 in the reference).  world_size == 1: a copy. */
+int pps_allgather(pps_handle* h, const double* in_host, int n, double* out_host);
+int pps_device_count(void);                                   /* CUDA devices visible to this process */
 
 #ifdef __cplusplus
 }

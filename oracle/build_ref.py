@@ -119,6 +119,33 @@ def _run(cmd):
         raise RuntimeError("command failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
 
 
+def build_dropin(name, force=False):
+    """The drop-in demonstration: the reference's own main.cpp + its own inputParam.hpp / solverSetup.hpp (config
+    <name>), compiled UNMODIFIED against include/reference_compat (GPU-backed solver classes) and linked with
+    libpps_b200.so  -> _ref/bin/ref_main_on_b200_<name>.  Returns "" when the library has not been built."""
+    root = os.path.dirname(HERE)
+    lib_dir = os.path.join(root, "parallelpoissonsolver_b200", "csrc")
+    if not os.path.exists(os.path.join(lib_dir, "libpps_b200.so")):
+        return ""
+    exe = os.path.join(OUT, "bin", "ref_main_on_b200_" + name)
+    if not force and os.path.exists(exe):
+        return exe
+    cfgdir = make_cfg_dir(name, CONFIGS[name])
+    only = os.path.join(cfgdir, "config_only")
+    os.makedirs(only, exist_ok=True)
+    for f in ("inputParam.hpp", "solverSetup.hpp"):
+        shutil.copyfile(os.path.join(cfgdir, f), os.path.join(only, f))
+    inc = ["-I" + os.path.join(root, "include", "reference_compat"), "-I" + os.path.join(root, "include"), "-I" + only]
+    obj = os.path.join(only, "ref_main_b200.o")
+    _run([CXX] + CXXFLAGS + inc + ["-Dmain=ref_main", "-c", os.path.join(REF_CPU, "src", "main.cpp"), "-o", obj])
+    _run([CXX] + CXXFLAGS + inc + [obj, os.path.join(root, "parallelpoissonsolver_b200", "driver", "ref_main_launcher.cpp"), "-o", exe,
+                                   "-L" + lib_dir, "-lpps_b200", "-Wl,-rpath," + lib_dir, "-Wl,-rpath,$ORIGIN/../../../parallelpoissonsolver_b200/csrc"])
+    return exe
+
+
+DROPIN_CONFIGS = ["default", "d64", "m24_cheb", "cg32"]
+
+
 def build_one(name, shim_obj, force=False):
     c = CONFIGS[name]
     bindir = os.path.join(OUT, "bin")
@@ -149,6 +176,7 @@ def build(names=None, force=False, jobs=None):
     names = list(names or CONFIGS)
     with ThreadPoolExecutor(max_workers=jobs or min(8, os.cpu_count() or 1)) as ex:
         res = list(ex.map(lambda n: build_one(n, shim_obj, force), names))
+        list(ex.map(lambda n: build_dropin(n, force), [n for n in DROPIN_CONFIGS if n in names]))
     return dict(zip(names, res))
 
 

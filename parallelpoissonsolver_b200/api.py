@@ -91,6 +91,9 @@ def load_library():
     L.pps_get_launch_count.argtypes = [P]
     L.pps_get_launch_count.restype = C.c_longlong
     L.pps_synchronize.argtypes = [P]
+    L.pps_set_max_iterations.argtypes = [P, C.c_int]
+    L.pps_allgather.argtypes = [P, D, C.c_int, D]
+    L.pps_device_count.restype = C.c_int
     _lib = L
     return L
 
@@ -299,3 +302,13 @@ class PoissonSolver:
 
     def synchronize(self):
         self._ck(self.L.pps_synchronize(self.h))
+
+    def set_max_iterations(self, n: int):
+        self._ck(self.L.pps_set_max_iterations(self.h, int(n)))
+
+    def allgather(self, values) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        out = np.zeros(v.size * self.world_size)
+        D = C.POINTER(C.c_double)
+        self._ck(self.L.pps_allgather(self.h, v.ctypes.data_as(D), v.size, out.ctypes.data_as(D)))
+        return out.reshape(self.world_size, v.size)

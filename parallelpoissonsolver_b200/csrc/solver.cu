@@ -1256,6 +1256,35 @@ int pps_get_kernel_stats(const pps_handle* h, int which, double* avg_ms, long lo
 
 long long pps_get_launch_count(const pps_handle* h) { return h->launch_count; }
 
+int pps_set_max_iterations(pps_handle* h, int max_iter) {
+    PPS_API_BEGIN
+    if (max_iter < 0 || max_iter + 2 > h->hist_len) throw std::runtime_error("max_iter exceeds the value the handle was created with");
+    h->cfg.max_iter = max_iter;
+    PPS_API_END
+}
+
+int pps_allgather(pps_handle* h, const double* in_host, int n, double* out_host) {
+    PPS_API_BEGIN
+    if (h->world == 1) {
+        std::memcpy(out_host, in_host, sizeof(double) * n);
+    } else {
+        PPS_CUDA_CHECK(cudaSetDevice(h->device));
+        if (static_cast<long long>(n) * h->world > h->partial_capacity) throw std::runtime_error("pps_allgather: too many values");
+        double* dev = h->partials;   // scratch: idle between solves
+        PPS_CUDA_CHECK(cudaMemcpyAsync(dev + static_cast<size_t>(h->rank) * n, in_host, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+        PPS_NCCL_CHECK(nccl().AllGather(dev + static_cast<size_t>(h->rank) * n, dev, n, ncclDouble, h->comm, h->stream));
+        PPS_CUDA_CHECK(cudaMemcpyAsync(out_host, dev, sizeof(double) * n * h->world, cudaMemcpyDeviceToHost, h->stream));
+        PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
+    PPS_API_END
+}
+
+int pps_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
 int pps_synchronize(pps_handle* h) {
     PPS_API_BEGIN
     PPS_CUDA_CHECK(cudaSetDevice(h->device));

@@ -1,0 +1,89 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity check, one process per GPU (run under torchrun; tests/test_gpu_multi.py drives it).
+
+    torchrun --nproc-per-node N tools/mg_check.py PX PY PZ [cheb] [cg]
+
+Every rank hosts its block of the PX x PY x PZ decomposition on its own GPU (NCCL halo exchange + allreduce);
+the CPU oracle runs the same layout in one process; rank 0 compares ||b||, the residual history and, after a
+gather, the solution.  Prints one JSON line and exits non-zero on mismatch.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import parallelpoissonsolver_b200 as pps  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+from tests import helpers as H  # noqa: E402
+
+
+def main():
+    px, py, pz = (int(v) for v in sys.argv[1:4])
+    flags = sys.argv[4:]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    assert px * py * pz == world
+    backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend, device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend)
+    dev = "cuda" if backend == "nccl" else "cpu"
+
+    np_ = (24 * px if px > 1 else 40, 20 * py if py > 1 else 24, 16 * pz if pz > 1 else 20)
+    ocfg = po.make_config(np_, (px, py, pz), ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), bcs=(0, 1, 0, 1, 0, 1),
+                          solver=po.SOLVER_CG if "cg" in flags else po.SOLVER_BICGSTAB,
+                          precond=po.PRECOND_CHEBYSHEV if "cheb" in flags else po.PRECOND_NONE, tolerance=1e-8)
+    if "cg" in flags:
+        ocfg.bcs[:] = [0] * 6
+    o = po.Oracle(ocfg)
+    o.set_problem()
+
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(pps.get_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, 0)
+    uid = bytes(t.cpu().numpy().tobytes())
+
+    s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, device=local), rank=rank, world_size=world, unique_id=uid)
+    H.hand_over_problem(o, s, ranks=[rank])
+    s.solve()
+    x = s.get_solution(rank)
+
+    # gather the per-rank data-range blocks on rank 0
+    mine = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, parts, dst=0)
+    ok = True
+    if rank == 0:
+        o.solve()
+        ho, hs = o.history(), s.history()
+        n10, n20 = min(11, len(ho), len(hs)), min(21, len(ho), len(hs))
+        d10 = float(np.max(np.abs(hs[:n10] - ho[:n10]) / ho[:n10]))
+        d20 = float(np.max(np.abs(hs[:n20] - ho[:n20]) / ho[:n20]))
+        blocks = [(list(o.block(r).nlocal), list(o.block(r).loc)) for r in range(world)]
+        xs = H.assemble_global([p.cpu().numpy() for p in parts], blocks, list(ocfg.np))
+        rel = H.rel_l2(xs, H.oracle_global_solution(o))
+        # guard planes after the final halo exchange (BiCGSTAB.hpp:317-321): my z- / x- guard = neighbour's data
+        out = dict(layout=[px, py, pz], flags=flags, iters=s.iterations, iters_oracle=o.iters, norm_b_rel=abs(s.norm_b - o.norm_b) / o.norm_b,
+                   hist10=d10, hist20=d20, sol_rel_l2=rel, true_residual=s.error_operator, seconds=s.solver_seconds)
+        ok = (out["norm_b_rel"] <= 1e-13 and d10 <= 1e-10 and d20 <= 1e-6 and rel <= 2e-6 and
+              0.9 * o.iters - 2 <= s.iterations <= 1.06 * o.iters + 2 and s.error_operator < 1.5e-8)
+        out["ok"] = bool(ok)
+        print(json.dumps(out), flush=True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    s.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()

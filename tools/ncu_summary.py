@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""Summarise ncu captures for profiles/:
+    python tools/ncu_summary.py launches <launches.csv>            -> per-kernel-class totals / shares (markdown)
+    python tools/ncu_summary.py full <a.ncu-rep> [b.ncu-rep ...]   -> key counters per captured launch (markdown)
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "l1tex__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
+        "sm__cycles_elapsed.max", "smsp__cycles_active.avg"]
+
+
+def short(name):
+    m = re.search(r"(stencil_tma_kernel|stencil_kernel|pointwise_kernel)<([^>]*(?:<[^>]*>)?[^>]*)>", name)
+    if m:
+        return m.group(1) + "<" + m.group(2) + ">"
+    return name.split("(")[0][:60]
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    h = rows[0]
+    ki, vi, ui = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        v = float(r[vi].replace(",", ""))
+        v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] in ("ms", "msecond") else v)
+        a = agg.setdefault(short(r[ki]), [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{k}` | {a[0]} | {a[1]:.1f} | {a[1] / a[0]:.1f} | {100 * a[1] / tot:.1f} % |")
+
+
+def full(paths):
+    for p in paths:
+        out = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        if len(rows) < 3:
+            continue
+        h, u = rows[0], rows[1]
+        for r in rows[2:]:
+            print(f"\n### `{short(r[h.index('Kernel Name')])}`  ({p.split('/')[-1]})\n\n| counter | value | unit |\n|---|---:|---|")
+            for k in KEYS:
+                if k in h:
+                    print(f"| {k} | {r[h.index(k)]} | {u[h.index(k)]} |")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2])
+    else:
+        full(sys.argv[2:])
