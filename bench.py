@@ -196,6 +196,52 @@ def workload_config(npglobal, n_gpus):
             "l2": "inputs larger than L2 (1.1 GB per vector per GPU, 7 vectors streamed per iteration)"}
 
 
+# ------------------------------------------------------------------------------------------------ rank plumbing
+class Dist:
+    """torch.distributed plumbing of the bench (NCCL on the GPU box; gloo in the CPU tests): barrier, max / sum over
+    ranks, broadcast of the NCCL unique id that libpps_b200.so needs for its own communicator."""
+
+    def __init__(self, rank, world, device):
+        self.rank, self.world, self.device = rank, world, device
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        if self.device != "cpu":
+            torch.cuda.synchronize()
+
+    def _reduce(self, v, op):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device=self.device)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, v):
+        import torch.distributed as dist
+        return self._reduce(v, dist.ReduceOp.MAX)
+
+    def sum(self, v):
+        import torch.distributed as dist
+        return self._reduce(v, dist.ReduceOp.SUM)
+
+    def bcast_bytes(self, payload, nbytes):
+        """rank 0's `payload` (bytes, length nbytes) on every rank"""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return payload
+        t = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        if self.rank == 0:
+            t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -205,6 +251,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--max-iter", type=int, default=6000)
+    ap.add_argument("--warmup-iters", type=int, default=100, help="iteration cap of the warm-up solves when N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -225,33 +272,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     uid = None
+    D = Dist(rank, world, "cuda")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            t.copy_(torch.frombuffer(bytearray(pps.get_unique_id()), dtype=torch.uint8))
-        dist.broadcast(t, 0)
-        uid = bytes(t.cpu().numpy().tobytes())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def rank_max(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def rank_sum(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        uid = D.bcast_bytes(pps.get_unique_id() if rank == 0 else None, 128)
+    barrier, rank_max, rank_sum = D.barrier, D.max, D.sum
 
     cfg = pps.make_config(npglobal, nranks=(1, 1, world), ds=(DS,) * 3, bcs=(0,) * 6, solver=pps.SOLVER_BICGSTAB,
                           precond=pps.PRECOND_NONE, tolerance=TOL, max_iter=args.max_iter, device=local_rank)
@@ -268,11 +294,15 @@ def main():
     solver.set_fields(my, xh, bh)
     solver.save_fields()
 
-    # ---- warm-up: full solves (the first also pays module load, NCCL channel setup, tensor-map encoding)
+    # ---- warm-up: untimed solves (module load, NCCL channel set-up, tensor-map encoding, clocks).  Full solves at
+    # N = 1; at N > 1 (1024^3, ~2800 iterations) they are capped at `--warmup-iters` iterations of the same loop.
+    if world > 1 and args.warmup_iters > 0:
+        solver.set_max_iterations(min(args.warmup_iters, args.max_iter))
     for _ in range(args.warmup):
         solver.restore_fields()
         barrier()
         solver.solve()
+    solver.set_max_iterations(args.max_iter)
     barrier()
 
     # ---- timed: K solves from HBM-resident fields; device time from the library's CUDA events, max over ranks
@@ -301,7 +331,7 @@ def main():
 
     # ---- end to end through the C ABI with host buffers (pinned): H2D of x and b, solve, D2H of x
     e2e_s = []
-    for _ in range(max(1, min(args.steps, 3))):
+    for _ in range(max(1, min(args.steps, 3)) if world == 1 else 1):
         barrier()
         t0 = time.perf_counter()
         solver.set_fields(my, xh, bh)
@@ -326,7 +356,7 @@ def main():
             "metric": "MLUP/s (cells*iterations/solve-seconds), Poisson solve to rel-res 1e-8", "value": value, "unit": "MLUP/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(npglobal, world),
+            "data": "synthetic", "config": dict(workload_config(npglobal, world), warmup_solves="full" if world == 1 else f"capped at {args.warmup_iters} iterations"),
             "iterations": iters_l, "solve_seconds": step_s, "true_residual": err_true,
             "e2e": {"value": cells * e2e_iters / float(np.mean(e2e_s)) / 1e6, "unit": "MLUP/s", "h2d_bytes_per_step": 2 * field_bytes * world,
                     "d2h_bytes_per_step": field_bytes * world, "seconds_per_step": float(np.mean(e2e_s)),
