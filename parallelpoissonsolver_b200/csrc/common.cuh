@@ -42,6 +42,21 @@ struct Box {
     int i0, i1, j0, j1, k0, k1;
 };
 
+// where the CTA grid of a launch starts: tile indices in x / y and the first z-plane (launches may cover any sub-box)
+struct TileOrigin {
+    int bx0, by0, kfirst;
+};
+
+// In-kernel wait for a halo exchange that runs concurrently on the halo stream (z-slab decompositions): the CTAs of
+// the first / last z-chunk are dispatched last (chunk index rotated by `shift`) and their TMA producer spins on
+// `flag` (set to `epoch` by the halo stream when the faces have landed) before it loads guard plane lo / hi.
+struct HaloWait {
+    const unsigned int* flag;   // nullptr: no waiting
+    unsigned int epoch;
+    int lo_plane, hi_plane;     // guard planes that are being received (-1: none)
+    int shift;                  // rotation of blockIdx.z
+};
+
 struct Coef {
     double ds[3];
     double ds2[3];     // ds*ds, as the reference evaluates it (matrixFreeOperatorA.hpp:35-37)

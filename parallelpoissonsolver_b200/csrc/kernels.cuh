@@ -194,15 +194,15 @@ struct CellMap {
 };
 
 template <int BY>
-__device__ __forceinline__ CellMap make_cellmap(const Dims& d, const Box& rg, int zchunk) {
+__device__ __forceinline__ CellMap make_cellmap(const Dims& d, const Box& rg, int zchunk, const TileOrigin& org) {
     CellMap m;
-    const int col = kFirstDataCol + 2 * (blockIdx.x * 32 + threadIdx.x);
-    const int j = 1 + blockIdx.y * BY + threadIdx.y;
+    const int col = kFirstDataCol + 2 * ((blockIdx.x + org.bx0) * 32 + threadIdx.x);
+    const int j = 1 + (blockIdx.y + org.by0) * BY + threadIdx.y;
     const int i0 = col - kOff;
     const bool jr = j >= rg.j0 && j < rg.j1;
     m.m0 = jr && i0 >= rg.i0 && i0 < rg.i1;
     m.m1 = jr && i0 + 1 >= rg.i0 && i0 + 1 < rg.i1;
-    const int kb = 1 + blockIdx.z * zchunk;
+    const int kb = org.kfirst + blockIdx.z * zchunk;
     m.kb = max(rg.k0, kb);
     m.ke = min(rg.k1, kb + zchunk);
     // lanes right of the row keep valid addresses; the first column right of the data range (the x+ guard)
@@ -220,13 +220,13 @@ __device__ __forceinline__ CellMap make_cellmap(const Dims& d, const Box& rg, in
 // ------------------------------------------------------------------------------------------------
 template <int BY, bool PARITY, class Epi>
 __global__ void __launch_bounds__(32 * BY) stencil_kernel(const double* __restrict__ u, Dims d, Box rg, Coef cf,
-                                                         int zchunk, Epi epi, RedCtx red, const Ctl* ctl) {
+                                                         int zchunk, TileOrigin org, Epi epi, RedCtx red, const Ctl* ctl) {
     if (ctl != nullptr && ctl->done) return;
     constexpr int NACC = Epi::NACC;
     double acc[NACC > 0 ? NACC : 1];
 #pragma unroll
     for (int a = 0; a < (NACC > 0 ? NACC : 1); a++) acc[a] = 0.0;
-    const CellMap m = make_cellmap<BY>(d, rg, zchunk);
+    const CellMap m = make_cellmap<BY>(d, rg, zchunk, org);
     if (m.warp_active) {
         const int lane = threadIdx.x;
         const double* up = u + m.rowoff;
@@ -395,13 +395,14 @@ struct EpiChebStep {
 // pointwise family (same tiling, no stencil): axpy updates fused with their reductions
 // ------------------------------------------------------------------------------------------------
 template <int BY, class Op>
-__global__ void __launch_bounds__(32 * BY) pointwise_kernel(Dims d, Box rg, int zchunk, Op op, RedCtx red, const Ctl* ctl) {
+__global__ void __launch_bounds__(32 * BY) pointwise_kernel(Dims d, Box rg, int zchunk, TileOrigin org, Op op, RedCtx red,
+                                                           const Ctl* ctl) {
     if (ctl != nullptr && ctl->done) return;
     constexpr int NACC = Op::NACC;
     double acc[NACC > 0 ? NACC : 1];
 #pragma unroll
     for (int a = 0; a < (NACC > 0 ? NACC : 1); a++) acc[a] = 0.0;
-    const CellMap m = make_cellmap<BY>(d, rg, zchunk);
+    const CellMap m = make_cellmap<BY>(d, rg, zchunk, org);
     if (m.warp_active && (m.m0 || m.m1)) {
         op.begin(ctl);
 #pragma unroll 4

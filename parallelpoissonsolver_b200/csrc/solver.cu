@@ -105,7 +105,15 @@ struct pps_handle {
     double* partials = nullptr;
     long long partial_capacity = 0;
     unsigned int* counter = nullptr;
-    ncclComm_t comm = nullptr;
+    ncclComm_t comm = nullptr;        // scalar allreduces, on the compute stream
+    ncclComm_t comm_halo = nullptr;   // face exchange, on the (high-priority) halo stream when overlap is on
+    cudaStream_t halo_stream = nullptr;
+    cudaEvent_t ev_field_ready = nullptr, ev_halo_done = nullptr;
+    int overlap = 1;                  // run the operator on the interior while the faces travel (world > 1)
+    unsigned int* halo_flag = nullptr;   // device: epoch of the last exchange that has landed
+    unsigned int halo_epoch = 0;
+    HaloWait wait_next{nullptr, 0, -1, -1, 0};   // consumed by the next TMA operator launch
+    int debug_no_halo = 0;            // timing experiments only: skip the exchange (wrong results)
     Coef coef{};
     // Chebyshev constants (chebyshevIteration.hpp:22-26)
     double theta = 0, delta = 0, sigma = 0;
@@ -206,28 +214,33 @@ static void check_launch(const char* what) {
 struct Tiling {
     dim3 grid, block;
     int zchunk;
+    TileOrigin org;
     unsigned int ctas() const { return grid.x * grid.y * grid.z; }
 };
 
+// CTA grid that covers `box` (any sub-box of the block): 64-wide x tiles, `by` rows, z-chunks
 static Tiling make_tiling(const pps_handle* h, const BlockGeom& g, const Box& box, bool stencil) {
     Tiling t;
     const bool tma = stencil && h->stencil_impl == 1;
     const int by = tma ? h->by_tma : h->by;
     t.block = dim3(32, tma ? by + 1 : by, 1);
-    const int gx = (g.n[0] + 63) / 64, gy = (g.n[1] + by - 1) / by;
+    const int bx0 = (std::max(box.i0, 1) - 1) / 64, bx1 = (std::min(box.i1, g.n[0] + 1) - 2) / 64 + 1;
+    const int by0 = (std::max(box.j0, 1) - 1) / by, by1 = (std::min(box.j1, g.n[1] + 1) - 2) / by + 1;
+    const int gx = std::max(1, bx1 - bx0), gy = std::max(1, by1 - by0);
+    const int nzb = std::max(1, box.k1 - box.k0);
     int zc = stencil ? h->zchunk_stencil : h->zchunk_point;
     if (zc <= 0) {
         // aim at ~6 waves of CTAs (148 SMs x 8 CTAs of 256 threads) but keep chunks >= 32 planes so that the
         // two extra planes a stencil chunk reads stay a few per cent of its traffic
         const long long target = 148LL * 8 * 6;
         long long nz_chunks = std::max<long long>(1, target / std::max(1, gx * gy));
-        zc = static_cast<int>((g.n[2] + nz_chunks - 1) / nz_chunks);
+        zc = static_cast<int>((nzb + nz_chunks - 1) / nz_chunks);
         zc = std::max(zc, stencil ? 32 : 8);
     }
-    zc = std::min(zc, std::max(1, g.n[2]));
+    zc = std::min(zc, nzb);
     t.zchunk = zc;
-    t.grid = dim3(gx, gy, (g.n[2] + zc - 1) / zc);
-    (void)box;
+    t.grid = dim3(gx, gy, (nzb + zc - 1) / zc);
+    t.org = TileOrigin{bx0, by0, box.k0};
     return t;
 }
 
@@ -300,7 +313,8 @@ static void launch_tma_inst(pps_handle* h, const Block& b, const double* u, cons
     const CUtensorMap& tm = tensor_map(h, b, u, BY, false);
     const CUtensorMap& a0 = Epi::NAUX > 0 ? tensor_map(h, b, epi.aux(0), BY, true) : tm;
     const CUtensorMap& a1 = Epi::NAUX > 1 ? tensor_map(h, b, epi.aux(1), BY, true) : tm;
-    kern<<<t.grid, t.block, smem, h->stream>>>(tm, a0, a1, b.g.dims, box, h->coef, t.zchunk, epi, red, ctl);
+    kern<<<t.grid, t.block, smem, h->stream>>>(tm, a0, a1, b.g.dims, box, h->coef, t.zchunk, t.org, h->wait_next, epi, red, ctl);
+    h->wait_next = HaloWait{nullptr, 0, -1, -1, 0};
 }
 
 template <class Epi>
@@ -318,7 +332,7 @@ static void launch_stencil(pps_handle* h, int kc, const Block& b, const double* 
         }
     } else {
 #define PPS_LAUNCH_ST(BYV, PAR) \
-    stencil_kernel<BYV, PAR, Epi><<<t.grid, t.block, 0, h->stream>>>(u, b.g.dims, box, h->coef, t.zchunk, epi, red, ctl)
+    stencil_kernel<BYV, PAR, Epi><<<t.grid, t.block, 0, h->stream>>>(u, b.g.dims, box, h->coef, t.zchunk, t.org, epi, red, ctl)
         if (h->by == 4) { if (h->parity) PPS_LAUNCH_ST(4, true); else PPS_LAUNCH_ST(4, false); }
         else            { if (h->parity) PPS_LAUNCH_ST(8, true); else PPS_LAUNCH_ST(8, false); }
 #undef PPS_LAUNCH_ST
@@ -334,8 +348,8 @@ static void launch_pointwise(pps_handle* h, int kc, const Block& b, const Box& b
     // pointwise ops read their scalars from ctl in begin(); the done check is skipped by passing a flag-free view
     const Ctl* ctl = h->ctl;
     (void)check_done;
-    if (h->by == 4) pointwise_kernel<4, Op><<<t.grid, t.block, 0, h->stream>>>(b.g.dims, box, t.zchunk, op, red, ctl);
-    else            pointwise_kernel<8, Op><<<t.grid, t.block, 0, h->stream>>>(b.g.dims, box, t.zchunk, op, red, ctl);
+    if (h->by == 4) pointwise_kernel<4, Op><<<t.grid, t.block, 0, h->stream>>>(b.g.dims, box, t.zchunk, t.org, op, red, ctl);
+    else            pointwise_kernel<8, Op><<<t.grid, t.block, 0, h->stream>>>(b.g.dims, box, t.zchunk, t.org, op, red, ctl);
     check_launch(kKernelNames[kc]);
     ls.count(1);
 }
@@ -373,12 +387,13 @@ static double* sel_p(Block& b) { return b.p; }
 static double* sel_mp(Block& b) { return b.mp; }
 static double* sel_z(Block& b) { return b.z; }
 
-// CommunicatorMPI::operator() + waitAllandCheckRcv (communicationMPI.hpp:51-316)
-static void halo_exchange(pps_handle* h, FieldSel sel, bool check_done) {
+// CommunicatorMPI::operator() + waitAllandCheckRcv (communicationMPI.hpp:51-316).  `on_halo_stream`: issue the
+// exchange on the high-priority halo stream with its own communicator (overlap with interior compute).
+static void halo_exchange(pps_handle* h, FieldSel sel, bool check_done, bool on_halo_stream = false) {
     bool any = false;
     for (auto& b : h->blocks)
         for (int f = 0; f < 6; f++) any = any || b.g.hc[f];
-    if (!any) return;
+    if (!any || h->debug_no_halo) return;
     LaunchScope ls(h, KC_HALO);
     const int ign = check_done ? 0 : 1;
     if (h->world == 1) {
@@ -396,12 +411,14 @@ static void halo_exchange(pps_handle* h, FieldSel sel, bool check_done) {
             }
         }
     } else {
+        cudaStream_t st = on_halo_stream ? h->halo_stream : h->stream;
+        ncclComm_t comm = on_halo_stream ? h->comm_halo : h->comm;
         Block& b = h->blocks[0];
         double* fld = sel(b);
         for (int f = 0; f < 4; f++) {   // x and y faces are strided: pack first
             if (!b.g.hc[f]) continue;
             FaceGeom g = face_geom(b.g, f, 1, 1);
-            face_pack_kernel<<<face_blocks(g), 256, 0, h->stream>>>(b.sendbuf[f], fld, g, h->ctl, ign);
+            face_pack_kernel<<<face_blocks(g), 256, 0, st>>>(b.sendbuf[f], fld, g, h->ctl, ign);
             ls.count(1);
         }
         PPS_NCCL_CHECK(nccl().GroupStart());
@@ -410,21 +427,21 @@ static void halo_exchange(pps_handle* h, FieldSel sel, bool check_done) {
             const int peer = b.g.nbr[f];
             if (f < 4) {
                 const size_t cnt = static_cast<size_t>(b.g.n[f / 2 == 0 ? 1 : 0]) * b.g.n[2];
-                PPS_NCCL_CHECK(nccl().Send(b.sendbuf[f], cnt, ncclDouble, peer, h->comm, h->stream));
-                PPS_NCCL_CHECK(nccl().Recv(b.recvbuf[f], cnt, ncclDouble, peer, h->comm, h->stream));
+                PPS_NCCL_CHECK(nccl().Send(b.sendbuf[f], cnt, ncclDouble, peer, comm, st));
+                PPS_NCCL_CHECK(nccl().Recv(b.recvbuf[f], cnt, ncclDouble, peer, comm, st));
             } else {
                 // z faces: a k-plane of the pitched layout is contiguous, padding and all -- no packing
                 const int up = f % 2;
                 const long long kdata = up ? b.g.n[2] : 1, kguard = up ? b.g.n[2] + 1 : 0;
-                PPS_NCCL_CHECK(nccl().Send(fld + kdata * b.g.dims.plane, b.g.dims.plane, ncclDouble, peer, h->comm, h->stream));
-                PPS_NCCL_CHECK(nccl().Recv(fld + kguard * b.g.dims.plane, b.g.dims.plane, ncclDouble, peer, h->comm, h->stream));
+                PPS_NCCL_CHECK(nccl().Send(fld + kdata * b.g.dims.plane, b.g.dims.plane, ncclDouble, peer, comm, st));
+                PPS_NCCL_CHECK(nccl().Recv(fld + kguard * b.g.dims.plane, b.g.dims.plane, ncclDouble, peer, comm, st));
             }
         }
         PPS_NCCL_CHECK(nccl().GroupEnd());
         for (int f = 0; f < 4; f++) {
             if (!b.g.hc[f]) continue;
             FaceGeom g = face_geom(b.g, f, 0, 0);
-            face_unpack_kernel<<<face_blocks(g), 256, 0, h->stream>>>(fld, b.recvbuf[f], g, h->ctl, ign);
+            face_unpack_kernel<<<face_blocks(g), 256, 0, st>>>(fld, b.recvbuf[f], g, h->ctl, ign);
             ls.count(1);
         }
     }
@@ -653,26 +670,92 @@ static void end_solve(pps_handle* h, bool reset_x_ghosts) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// halo exchange + Neumann ghosts + fused operator + scalar reduction: the block that BiCGSTAB.hpp:135-164 /
+// :182-225 / baseCG.hpp:118-151 repeat.  With one block per GPU (world > 1) the faces travel on the halo
+// stream while the operator runs on the interior box; the boundary shell (one cell thick on every face that
+// has a neighbour) is launched after the exchange has landed.  All launches feed one ticket reduction.
+// ------------------------------------------------------------------------------------------------
+static void split_box(const BlockGeom& g, const Box& box, Box& inner, std::vector<Box>& shell) {
+    inner = box;
+    if (g.hc[4]) { shell.push_back(Box{box.i0, box.i1, box.j0, box.j1, inner.k0, inner.k0 + 1}); inner.k0 += 1; }
+    if (g.hc[5]) { shell.push_back(Box{box.i0, box.i1, box.j0, box.j1, inner.k1 - 1, inner.k1}); inner.k1 -= 1; }
+    if (g.hc[2]) { shell.push_back(Box{box.i0, box.i1, inner.j0, inner.j0 + 1, inner.k0, inner.k1}); inner.j0 += 1; }
+    if (g.hc[3]) { shell.push_back(Box{box.i0, box.i1, inner.j1 - 1, inner.j1, inner.k0, inner.k1}); inner.j1 -= 1; }
+    if (g.hc[0]) { shell.push_back(Box{inner.i0, inner.i0 + 1, inner.j0, inner.j1, inner.k0, inner.k1}); inner.i0 += 1; }
+    if (g.hc[1]) { shell.push_back(Box{inner.i1 - 1, inner.i1, inner.j0, inner.j1, inner.k0, inner.k1}); inner.i1 -= 1; }
+}
+static bool box_empty(const Box& b) { return b.i0 >= b.i1 || b.j0 >= b.j1 || b.k0 >= b.k1; }
+
+template <class MakeEpi>
+static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int nacc, int op, MakeEpi make_epi) {
+    bool any_comm = false;
+    for (int f = 0; f < 6; f++) any_comm = any_comm || h->blocks[0].g.hc[f];
+    const bool overlap = h->world > 1 && h->overlap && !h->debug_no_halo && any_comm;
+    if (!overlap) {
+        halo_exchange(h, sel, true);
+        const unsigned int total = total_ctas(h, true);
+        unsigned int off = 0;
+        for (auto& b : h->blocks) {
+            if (ghosts) neumann_ghosts(h, b, sel(b), false, true);
+            const Box box = b.g.solver_box();
+            const Tiling t = make_tiling(h, b.g, box, true);
+            RedCtx red = make_red(h, nacc, total, off, op);
+            launch_stencil(h, kc, b, sel(b), box, make_epi(b), red, t, true);
+            off += t.ctas();
+        }
+    } else {
+        Block& b = h->blocks[0];
+        PPS_CUDA_CHECK(cudaEventRecord(h->ev_field_ready, h->stream));
+        PPS_CUDA_CHECK(cudaStreamWaitEvent(h->halo_stream, h->ev_field_ready, 0));
+        halo_exchange(h, sel, true, /*on_halo_stream=*/true);
+        const bool z_only = !(b.g.hc[0] || b.g.hc[1] || b.g.hc[2] || b.g.hc[3]);
+        if (ghosts) neumann_ghosts(h, b, sel(b), false, true);
+        const Tiling t_all = make_tiling(h, b.g, b.g.solver_box(), true);
+        if (z_only && h->stencil_impl == 1 && h->overlap == 1 && t_all.grid.z >= 3) {
+            // slabs: ONE launch; the first / last z-chunk run last and their TMA producer waits in-kernel for the faces
+            h->halo_epoch++;
+            publish_halo_epoch_kernel<<<1, 1, 0, h->halo_stream>>>(h->halo_flag, h->halo_epoch);
+            const Box box = b.g.solver_box();
+            const Tiling t = t_all;
+            h->wait_next = HaloWait{h->halo_flag, h->halo_epoch, b.g.hc[4] ? 0 : -1, b.g.hc[5] ? b.g.n[2] + 1 : -1,
+                                    (b.g.hc[4] && t.grid.z > 1) ? 1 : 0};
+            RedCtx red = make_red(h, nacc, t.ctas(), 0, op);
+            launch_stencil(h, kc, b, sel(b), box, make_epi(b), red, t, true);
+        } else {
+            // general case: interior box now, the one-cell shell after the exchange has landed
+            PPS_CUDA_CHECK(cudaEventRecord(h->ev_halo_done, h->halo_stream));
+            Box inner;
+            std::vector<Box> shell;
+            split_box(b.g, b.g.solver_box(), inner, shell);
+            std::vector<Box> boxes;
+            if (!box_empty(inner)) boxes.push_back(inner);
+            const size_t n_inner = boxes.size();
+            for (auto& sb : shell)
+                if (!box_empty(sb)) boxes.push_back(sb);
+            std::vector<Tiling> tl;
+            unsigned int total = 0;
+            for (auto& bx : boxes) { tl.push_back(make_tiling(h, b.g, bx, true)); total += tl.back().ctas(); }
+            unsigned int off = 0;
+            for (size_t q = 0; q < boxes.size(); q++) {
+                if (q == n_inner) PPS_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_halo_done, 0));
+                RedCtx red = make_red(h, nacc, total, off, op);
+                launch_stencil(h, kc, b, sel(b), boxes[q], make_epi(b), red, tl[q], true);
+                off += tl[q].ctas();
+            }
+            if (n_inner == boxes.size()) PPS_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_halo_done, 0));
+        }
+    }
+    if (nacc > 0) finish_reduction(h, nacc, op, false);
+}
+
+// ------------------------------------------------------------------------------------------------
 // BiCGSTAB (BiCGSTAB.hpp:55-322), isMainLoop = true, communicationON = true
 // ------------------------------------------------------------------------------------------------
 static void bicgstab_iteration(pps_handle* h) {
     const bool parity = h->parity;
-    // Mp = M(p); halo(Mp); ghosts(Mp)                                       :133-140
+    // Mp = M(p); halo(Mp); ghosts(Mp); v = A Mp; sum r0.v; alpha             :133-164
     for (auto& b : h->blocks) precondition(h, b, b.mp, b.p, true);
-    halo_exchange(h, sel_mp, true);
-    {
-        const unsigned int total = total_ctas(h, true);
-        unsigned int off = 0;
-        for (auto& b : h->blocks) {
-            neumann_ghosts(h, b, b.mp, false, true);
-            const Box box = b.g.solver_box();
-            const Tiling t = make_tiling(h, b.g, box, true);
-            RedCtx red = make_red(h, 1, total, off, OP_BICG_ALPHA);
-            launch_stencil(h, KC_APPLY_DOT, b, b.mp, box, EpiStoreDot{b.v, b.r0}, red, t, true);   // :142-155
-            off += t.ctas();
-        }
-        finish_reduction(h, 1, OP_BICG_ALPHA, false);                         // :156-164
-    }
+    fused_operator(h, KC_APPLY_DOT, sel_mp, true, 1, OP_BICG_ALPHA, [](Block& b) { return EpiStoreDot{b.v, b.r0}; });
     for (auto& b : h->blocks) {                                               // :168-178
         const Box box = b.g.solver_box();
         const Tiling t = make_tiling(h, b.g, box, false);
@@ -680,23 +763,12 @@ static void bicgstab_iteration(pps_handle* h) {
         if (parity) launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<true>{b.r, b.v, 0}, red, t, true);
         else        launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<false>{b.r, b.v, 0}, red, t, true);
     }
-    // z = M(r); halo(z); ghosts(z)                                          :181-188
+    // z = M(r); halo(z); ghosts(z); t = A z; sum r.t, t.t; omega             :181-225
     for (auto& b : h->blocks) precondition(h, b, b.z, b.r, true);
-    halo_exchange(h, sel_z, true);
-    {
-        const unsigned int total = total_ctas(h, true);
-        unsigned int off = 0;
-        for (auto& b : h->blocks) {
-            neumann_ghosts(h, b, b.z, false, true);
-            const Box box = b.g.solver_box();
-            const Tiling t = make_tiling(h, b.g, box, true);
-            RedCtx red = make_red(h, 2, total, off, OP_BICG_OMEGA);
-            if (b.z == b.r) launch_stencil(h, KC_APPLY_DOT2, b, b.z, box, EpiStoreDot2Self{b.t}, red, t, true);   // :189-214
-            else            launch_stencil(h, KC_APPLY_DOT2, b, b.z, box, EpiStoreDot2{b.t, b.r}, red, t, true);
-            off += t.ctas();
-        }
-        finish_reduction(h, 2, OP_BICG_OMEGA, false);                         // :216-225
-    }
+    if (h->blocks[0].z == h->blocks[0].r)
+        fused_operator(h, KC_APPLY_DOT2, sel_z, true, 2, OP_BICG_OMEGA, [](Block& b) { return EpiStoreDot2Self{b.t}; });
+    else
+        fused_operator(h, KC_APPLY_DOT2, sel_z, true, 2, OP_BICG_OMEGA, [](Block& b) { return EpiStoreDot2{b.t, b.r}; });
     {
         const unsigned int total = total_ctas(h, false);
         unsigned int off = 0;
@@ -721,20 +793,11 @@ static void bicgstab_iteration(pps_handle* h) {
 
 static void cg_iteration(pps_handle* h) {
     const bool parity = h->parity;
-    halo_exchange(h, sel_p, true);                                            // baseCG.hpp:118-122 (no ghost reset for order 2)
-    {
-        const unsigned int total = total_ctas(h, true);
-        unsigned int off = 0;
-        for (auto& b : h->blocks) {
-            const Box box = b.g.solver_box();
-            const Tiling t = make_tiling(h, b.g, box, true);
-            RedCtx red = make_red(h, 2, total, off, OP_CG_ALPHA);
-            if (b.z == b.r) launch_stencil(h, KC_CG_APPLY, b, b.p, box, EpiCgApplySelf{b.v, b.r}, red, t, true);   // :126-140
-            else            launch_stencil(h, KC_CG_APPLY, b, b.p, box, EpiCgApply{b.v, b.r, b.z}, red, t, true);
-            off += t.ctas();
-        }
-        finish_reduction(h, 2, OP_CG_ALPHA, false);
-    }
+    // halo(p) (no ghost reset for order 2, baseCG.hpp:123-124); Ap = A p; sum r.z, p.Ap; alpha     :118-151
+    if (h->blocks[0].z == h->blocks[0].r)
+        fused_operator(h, KC_CG_APPLY, sel_p, false, 2, OP_CG_ALPHA, [](Block& b) { return EpiCgApplySelf{b.v, b.r}; });
+    else
+        fused_operator(h, KC_CG_APPLY, sel_p, false, 2, OP_CG_ALPHA, [](Block& b) { return EpiCgApply{b.v, b.r, b.z}; });
     const bool none = h->cfg.precond == PPS_PRECOND_NONE;
     {
         const unsigned int total = total_ctas(h, false);
@@ -807,6 +870,7 @@ static void solve(pps_handle* h) {
     end_solve(h, /*reset_x_ghosts=*/!cg);
     PPS_CUDA_CHECK(cudaEventRecord(h->ev_end, h->stream));
     PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (h->halo_stream) PPS_CUDA_CHECK(cudaStreamSynchronize(h->halo_stream));   // exchanges of iterations launched past convergence
     float ms = 0;
     PPS_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev_loop0, h->ev_loop1));
     h->loop_seconds = ms * 1e-3;
@@ -862,6 +926,8 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     h->zchunk_stencil = env_int("PPS_ZCHUNK_STENCIL", 0);
     h->zchunk_point = env_int("PPS_ZCHUNK_POINT", 0);
     h->lag = env_int("PPS_LAG", 3);
+    h->overlap = env_int("PPS_OVERLAP", 1);
+    h->debug_no_halo = env_int("PPS_DEBUG_NO_HALO", 0);
     PPS_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (int d = 0; d < 3; d++) {
         h->coef.ds[d] = cfg.ds[d];
@@ -925,6 +991,16 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         static_assert(sizeof(ncclUniqueId) <= PPS_UNIQUE_ID_BYTES, "unique id size");
         std::memcpy(&id, uid, sizeof(id));
         PPS_NCCL_CHECK(nccl().CommInitRank(&h->comm, world, id, rank));
+        // a second communicator for the faces, so that exchanges on the halo stream never interleave with the
+        // scalar allreduces on the compute stream
+        PPS_NCCL_CHECK(nccl().CommSplit(h->comm, 0, rank, &h->comm_halo, nullptr));
+        int lo = 0, hi = 0;
+        PPS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PPS_CUDA_CHECK(cudaStreamCreateWithPriority(&h->halo_stream, cudaStreamNonBlocking, hi));
+        PPS_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_field_ready, cudaEventDisableTiming));
+        PPS_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_halo_done, cudaEventDisableTiming));
+        PPS_CUDA_CHECK(cudaMalloc(&h->halo_flag, sizeof(unsigned int)));
+        PPS_CUDA_CHECK(cudaMemsetAsync(h->halo_flag, 0, sizeof(unsigned int), h->stream));
     }
     h->ctl_host = Ctl{};
     h->ctl_host.norm_b = 1;
@@ -937,7 +1013,13 @@ static void destroy(pps_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->halo_stream) cudaStreamSynchronize(h->halo_stream);
+    if (h->comm_halo) nccl().CommDestroy(h->comm_halo);
     if (h->comm) nccl().CommDestroy(h->comm);
+    if (h->halo_stream) cudaStreamDestroy(h->halo_stream);
+    if (h->ev_field_ready) cudaEventDestroy(h->ev_field_ready);
+    if (h->ev_halo_done) cudaEventDestroy(h->ev_halo_done);
+    if (h->halo_flag) cudaFree(h->halo_flag);
     for (auto& b : h->blocks)
         for (double* p : b.owned) cudaFree(p);
     cudaFree(h->partials);

@@ -57,6 +57,22 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
+// spin until the halo stream has published `epoch` (monotonic counter), then order the following bulk-tensor read
+// (async proxy) after the acquire
+__device__ __forceinline__ void wait_halo_flag(const unsigned int* flag, unsigned int epoch) {
+    unsigned int v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (static_cast<int>(v - epoch) >= 0) break;
+        __nanosleep(200);
+    } while (true);
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+__global__ void publish_halo_epoch_kernel(unsigned int* flag, unsigned int epoch) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+
 template <int BY, int STAGES, int NAUX>
 struct TmaSmem {
     static constexpr int kMainElems = kTmaBoxX * (BY + 2);
@@ -71,7 +87,8 @@ template <int BY, int STAGES, bool PARITY, class Epi>
 __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                    const __grid_constant__ CUtensorMap tmap_a0,
                                                                    const __grid_constant__ CUtensorMap tmap_a1, Dims d, Box rg,
-                                                                   Coef cf, int zchunk, Epi epi, RedCtx red, const Ctl* ctl) {
+                                                                   Coef cf, int zchunk, TileOrigin org, HaloWait hw, Epi epi,
+                                                                   RedCtx red, const Ctl* ctl) {
     if (ctl != nullptr && ctl->done) return;
     constexpr int NACC = Epi::NACC;
     constexpr int NAUX = Epi::NAUX;
@@ -83,9 +100,10 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid
     uint64_t* empty = full + STAGES;
 
     const int lane = threadIdx.x, warp = threadIdx.y;
-    const int col0 = kFirstDataCol + 64 * blockIdx.x;
-    const int y0 = 1 + BY * blockIdx.y;
-    const int kchunk = 1 + blockIdx.z * zchunk;
+    const int col0 = kFirstDataCol + 64 * (blockIdx.x + org.bx0);
+    const int y0 = 1 + BY * (blockIdx.y + org.by0);
+    const int zidx = hw.shift ? static_cast<int>((blockIdx.z + hw.shift) % gridDim.z) : static_cast<int>(blockIdx.z);
+    const int kchunk = org.kfirst + zidx * zchunk;
     const int kb = max(rg.k0, kchunk), ke = min(rg.k1, kchunk + zchunk);
     const int nplanes = ke - kb + 2;   // planes kb-1 .. ke
 
@@ -112,8 +130,10 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid
                     double* dst = ring + s * SM::kStageElems;
                     // aux streams are only read where the operator is evaluated: planes kb .. ke-1
                     const bool with_aux = NAUX > 0 && p >= 1 && p <= nplanes - 2;
+                    const int kk = kb - 1 + p;
+                    if (hw.flag != nullptr && (kk == hw.lo_plane || kk == hw.hi_plane)) wait_halo_flag(hw.flag, hw.epoch);
                     mbar_arrive_expect_tx(&full[s], with_aux ? SM::kStageBytes : SM::kMainBytes);
-                    tma_load_3d(dst, &tmap, &full[s], col0 - kTmaLead, y0 - 1, kb - 1 + p);
+                    tma_load_3d(dst, &tmap, &full[s], col0 - kTmaLead, y0 - 1, kk);
                     if (with_aux) {
                         if (NAUX > 0) tma_load_3d(dst + SM::kMainElems, &tmap_a0, &full[s], col0, y0, kb - 1 + p);
                         if (NAUX > 1) tma_load_3d(dst + SM::kMainElems + SM::kAuxElems, &tmap_a1, &full[s], col0, y0, kb - 1 + p);
