@@ -108,8 +108,11 @@ struct pps_handle {
     ncclComm_t comm = nullptr;        // scalar allreduces, on the compute stream
     ncclComm_t comm_halo = nullptr;   // face exchange, on the (high-priority) halo stream when overlap is on
     cudaStream_t halo_stream = nullptr;
+    cudaStream_t bnd_stream = nullptr;   // boundary-shell launches of an overlapped operator, concurrent with the interior launch
+    cudaStream_t launch_stream = nullptr;   // stream the operator launchers use right now (stream or bnd_stream)
+    cudaEvent_t ev_pre = nullptr, ev_bnd_done = nullptr;
     cudaEvent_t ev_field_ready = nullptr, ev_halo_done = nullptr;
-    int overlap = 1;                  // run the operator on the interior while the faces travel (world > 1)
+    int overlap = 1;                  // 0 serial; 1 interior first, boundary chunks after the exchange; 2 in-kernel wait (experimental)
     unsigned int* halo_flag = nullptr;   // device: epoch of the last exchange that has landed
     unsigned int halo_epoch = 0;
     HaloWait wait_next{nullptr, 0, -1, -1, 0};   // consumed by the next TMA operator launch
@@ -230,12 +233,17 @@ static Tiling make_tiling(const pps_handle* h, const BlockGeom& g, const Box& bo
     const int nzb = std::max(1, box.k1 - box.k0);
     int zc = stencil ? h->zchunk_stencil : h->zchunk_point;
     if (zc <= 0) {
-        // aim at ~6 waves of CTAs (148 SMs x 8 CTAs of 256 threads) but keep chunks >= 32 planes so that the
-        // two extra planes a stencil chunk reads stay a few per cent of its traffic
-        const long long target = 148LL * 8 * 6;
-        long long nz_chunks = std::max<long long>(1, target / std::max(1, gx * gy));
-        zc = static_cast<int>((nzb + nz_chunks - 1) / nz_chunks);
-        zc = std::max(zc, stencil ? 32 : 8);
+        if (stencil) {
+            // measured on B200 at 512^3 (profiles/r01_stencil_sweep.md): 16..32 planes per chunk is best (6.2 / 6.0 TB/s),
+            // 64 -> 5.7, 128 -> 5.3, 512 -> 4.6 TB/s: short chunks balance the waves and the two extra planes a chunk
+            // reads are still in L2 from the neighbouring chunk (z is the slowest grid dimension)
+            zc = 32;
+        } else {
+            // pointwise kernels have no halo: ~6 waves of CTAs (148 SMs x 8 CTAs of 256 threads), chunks >= 8 planes
+            const long long target = 148LL * 8 * 6;
+            long long nz_chunks = std::max<long long>(1, target / std::max(1, gx * gy));
+            zc = std::max(static_cast<int>((nzb + nz_chunks - 1) / nz_chunks), 8);
+        }
     }
     zc = std::min(zc, nzb);
     t.zchunk = zc;
@@ -313,7 +321,7 @@ static void launch_tma_inst(pps_handle* h, const Block& b, const double* u, cons
     const CUtensorMap& tm = tensor_map(h, b, u, BY, false);
     const CUtensorMap& a0 = Epi::NAUX > 0 ? tensor_map(h, b, epi.aux(0), BY, true) : tm;
     const CUtensorMap& a1 = Epi::NAUX > 1 ? tensor_map(h, b, epi.aux(1), BY, true) : tm;
-    kern<<<t.grid, t.block, smem, h->stream>>>(tm, a0, a1, b.g.dims, box, h->coef, t.zchunk, t.org, h->wait_next, epi, red, ctl);
+    kern<<<t.grid, t.block, smem, h->launch_stream>>>(tm, a0, a1, b.g.dims, box, h->coef, t.zchunk, t.org, h->wait_next, epi, red, ctl);
     h->wait_next = HaloWait{nullptr, 0, -1, -1, 0};
 }
 
@@ -332,7 +340,7 @@ static void launch_stencil(pps_handle* h, int kc, const Block& b, const double* 
         }
     } else {
 #define PPS_LAUNCH_ST(BYV, PAR) \
-    stencil_kernel<BYV, PAR, Epi><<<t.grid, t.block, 0, h->stream>>>(u, b.g.dims, box, h->coef, t.zchunk, t.org, epi, red, ctl)
+    stencil_kernel<BYV, PAR, Epi><<<t.grid, t.block, 0, h->launch_stream>>>(u, b.g.dims, box, h->coef, t.zchunk, t.org, epi, red, ctl)
         if (h->by == 4) { if (h->parity) PPS_LAUNCH_ST(4, true); else PPS_LAUNCH_ST(4, false); }
         else            { if (h->parity) PPS_LAUNCH_ST(8, true); else PPS_LAUNCH_ST(8, false); }
 #undef PPS_LAUNCH_ST
@@ -675,10 +683,14 @@ static void end_solve(pps_handle* h, bool reset_x_ghosts) {
 // stream while the operator runs on the interior box; the boundary shell (one cell thick on every face that
 // has a neighbour) is launched after the exchange has landed.  All launches feed one ticket reduction.
 // ------------------------------------------------------------------------------------------------
-static void split_box(const BlockGeom& g, const Box& box, Box& inner, std::vector<Box>& shell) {
+// `tz`: thickness of the z shells.  One plane would do, but a CTA that computes one plane still streams three; whole
+// z-chunks keep the boundary launches as efficient as the interior one.
+static void split_box(const BlockGeom& g, const Box& box, int tz, Box& inner, std::vector<Box>& shell) {
     inner = box;
-    if (g.hc[4]) { shell.push_back(Box{box.i0, box.i1, box.j0, box.j1, inner.k0, inner.k0 + 1}); inner.k0 += 1; }
-    if (g.hc[5]) { shell.push_back(Box{box.i0, box.i1, box.j0, box.j1, inner.k1 - 1, inner.k1}); inner.k1 -= 1; }
+    const int nzb = box.k1 - box.k0;
+    tz = std::max(1, std::min(tz, nzb / 3));
+    if (g.hc[4]) { shell.push_back(Box{box.i0, box.i1, box.j0, box.j1, inner.k0, inner.k0 + tz}); inner.k0 += tz; }
+    if (g.hc[5]) { shell.push_back(Box{box.i0, box.i1, box.j0, box.j1, inner.k1 - tz, inner.k1}); inner.k1 -= tz; }
     if (g.hc[2]) { shell.push_back(Box{box.i0, box.i1, inner.j0, inner.j0 + 1, inner.k0, inner.k1}); inner.j0 += 1; }
     if (g.hc[3]) { shell.push_back(Box{box.i0, box.i1, inner.j1 - 1, inner.j1, inner.k0, inner.k1}); inner.j1 -= 1; }
     if (g.hc[0]) { shell.push_back(Box{inner.i0, inner.i0 + 1, inner.j0, inner.j1, inner.k0, inner.k1}); inner.i0 += 1; }
@@ -711,8 +723,10 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
         const bool z_only = !(b.g.hc[0] || b.g.hc[1] || b.g.hc[2] || b.g.hc[3]);
         if (ghosts) neumann_ghosts(h, b, sel(b), false, true);
         const Tiling t_all = make_tiling(h, b.g, b.g.solver_box(), true);
-        if (z_only && h->stencil_impl == 1 && h->overlap == 1 && t_all.grid.z >= 3) {
-            // slabs: ONE launch; the first / last z-chunk run last and their TMA producer waits in-kernel for the faces
+        if (z_only && h->stencil_impl == 1 && h->overlap == 2 && t_all.grid.z >= 3) {
+            // EXPERIMENTAL (PPS_OVERLAP=2): ONE launch; the first / last z-chunk run last and their TMA producer waits in-kernel
+            // for the faces.  Fastest when it works, but it needs the NCCL kernel to become resident while waiting CTAs hold
+            // the SMs -- CUDA gives no such forward-progress guarantee (it deadlocked on 8 GPUs), hence not the default.
             h->halo_epoch++;
             publish_halo_epoch_kernel<<<1, 1, 0, h->halo_stream>>>(h->halo_flag, h->halo_epoch);
             const Box box = b.g.solver_box();
@@ -722,11 +736,13 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
             RedCtx red = make_red(h, nacc, t.ctas(), 0, op);
             launch_stencil(h, kc, b, sel(b), box, make_epi(b), red, t, true);
         } else {
-            // general case: interior box now, the one-cell shell after the exchange has landed
+            // interior box on the compute stream now; the boundary shell on its own stream as soon as the faces have
+            // landed -- both launches share the GPU (no serialisation, no in-kernel waiting) and feed one ticket reduction
             PPS_CUDA_CHECK(cudaEventRecord(h->ev_halo_done, h->halo_stream));
+            PPS_CUDA_CHECK(cudaEventRecord(h->ev_pre, h->stream));   // field updated, Neumann ghosts written
             Box inner;
             std::vector<Box> shell;
-            split_box(b.g, b.g.solver_box(), inner, shell);
+            split_box(b.g, b.g.solver_box(), t_all.zchunk, inner, shell);
             std::vector<Box> boxes;
             if (!box_empty(inner)) boxes.push_back(inner);
             const size_t n_inner = boxes.size();
@@ -737,12 +753,19 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
             for (auto& bx : boxes) { tl.push_back(make_tiling(h, b.g, bx, true)); total += tl.back().ctas(); }
             unsigned int off = 0;
             for (size_t q = 0; q < boxes.size(); q++) {
-                if (q == n_inner) PPS_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_halo_done, 0));
+                if (q == n_inner) {
+                    PPS_CUDA_CHECK(cudaStreamWaitEvent(h->bnd_stream, h->ev_pre, 0));
+                    PPS_CUDA_CHECK(cudaStreamWaitEvent(h->bnd_stream, h->ev_halo_done, 0));
+                    h->launch_stream = h->bnd_stream;
+                }
                 RedCtx red = make_red(h, nacc, total, off, op);
                 launch_stencil(h, kc, b, sel(b), boxes[q], make_epi(b), red, tl[q], true);
                 off += tl[q].ctas();
             }
-            if (n_inner == boxes.size()) PPS_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_halo_done, 0));
+            h->launch_stream = h->stream;
+            PPS_CUDA_CHECK(cudaEventRecord(h->ev_bnd_done, h->bnd_stream));
+            PPS_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_bnd_done, 0));
+            PPS_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_halo_done, 0));
         }
     }
     if (nacc > 0) finish_reduction(h, nacc, op, false);
@@ -871,6 +894,7 @@ static void solve(pps_handle* h) {
     PPS_CUDA_CHECK(cudaEventRecord(h->ev_end, h->stream));
     PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     if (h->halo_stream) PPS_CUDA_CHECK(cudaStreamSynchronize(h->halo_stream));   // exchanges of iterations launched past convergence
+    if (h->bnd_stream) PPS_CUDA_CHECK(cudaStreamSynchronize(h->bnd_stream));
     float ms = 0;
     PPS_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev_loop0, h->ev_loop1));
     h->loop_seconds = ms * 1e-3;
@@ -929,6 +953,7 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     h->overlap = env_int("PPS_OVERLAP", 1);
     h->debug_no_halo = env_int("PPS_DEBUG_NO_HALO", 0);
     PPS_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->launch_stream = h->stream;
     for (int d = 0; d < 3; d++) {
         h->coef.ds[d] = cfg.ds[d];
         h->coef.ds2[d] = cfg.ds[d] * cfg.ds[d];
@@ -997,6 +1022,9 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         int lo = 0, hi = 0;
         PPS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         PPS_CUDA_CHECK(cudaStreamCreateWithPriority(&h->halo_stream, cudaStreamNonBlocking, hi));
+        PPS_CUDA_CHECK(cudaStreamCreateWithPriority(&h->bnd_stream, cudaStreamNonBlocking, hi));
+        PPS_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
+        PPS_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_bnd_done, cudaEventDisableTiming));
         PPS_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_field_ready, cudaEventDisableTiming));
         PPS_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_halo_done, cudaEventDisableTiming));
         PPS_CUDA_CHECK(cudaMalloc(&h->halo_flag, sizeof(unsigned int)));
@@ -1017,6 +1045,9 @@ static void destroy(pps_handle* h) {
     if (h->comm_halo) nccl().CommDestroy(h->comm_halo);
     if (h->comm) nccl().CommDestroy(h->comm);
     if (h->halo_stream) cudaStreamDestroy(h->halo_stream);
+    if (h->bnd_stream) cudaStreamDestroy(h->bnd_stream);
+    if (h->ev_pre) cudaEventDestroy(h->ev_pre);
+    if (h->ev_bnd_done) cudaEventDestroy(h->ev_bnd_done);
     if (h->ev_field_ready) cudaEventDestroy(h->ev_field_ready);
     if (h->ev_halo_done) cudaEventDestroy(h->ev_halo_done);
     if (h->halo_flag) cudaFree(h->halo_flag);
