@@ -118,6 +118,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic_per_cell(kernel="xr_update"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per cell of the dominant kernel, from the committed ncu capture"""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        t = json.load(open(p))[kernel]
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["cells"]
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -390,6 +400,7 @@ def main():
     dom_avg_ms = dom_ms / max(1, dom_n)
     achieved = 7 * 8 * slab_cells / dom_avg_ms / 1e6 if dom_avg_ms > 0 else None
     iter_gbs = 136 * slab_cells * total_iters / float(np.sum(loop_s)) / 1e9
+    tpc = measured_traffic_per_cell()
 
     if rank == 0:
         line = {
@@ -404,7 +415,10 @@ def main():
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "xr_update (x+=alpha*p+omega*s; r=s-omega*t; r0.r; r.r), 7 vector passes = 56 B/cell",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / peak if achieved else None, "traffic": None, "launches_timed": dom_n, "avg_ms": dom_avg_ms},
+                         "frac": achieved / peak if achieved else None,
+                         "algorithmic_bytes_per_launch": 56 * slab_cells,
+                         "traffic": tpc * slab_cells if tpc else None, "traffic_source": "profiles/r01_traffic.json (ncu --set full, 512^3), scaled by cells per launch",
+                         "launches_timed": dom_n, "avg_ms": dom_avg_ms},
             "roofline_iteration": {"bound": "hbm", "what": "whole BiCGSTAB iteration, 136 algorithmic B/cell (17 passes; 19 are moved)",
                                    "achieved": iter_gbs, "peak": peak, "unit": "GB/s", "frac": iter_gbs / peak},
         }
