@@ -22,6 +22,7 @@
 #include "communicationMPI.hpp"
 #include "matrixFreeOperatorA.hpp"
 #include "mpi.h"
+#include "output.hpp"
 #include "solverSetup.hpp"
 
 namespace pps_compat {
@@ -76,6 +77,7 @@ class SolverAdapter {
         c.order_neumann = orderNeumanBcs;
         if (const char* a = std::getenv("PPS_ARITHMETIC")) c.arithmetic = std::atoi(a);
         cfg_ = c;
+        precondIterations_ = precond.precond_kind == PPS_PRECOND_CHEBYSHEV ? precond.iterations : 0;
         World& w = world();
         const int ngpu = pps_device_count();
         if (nranksTot_ == 1) {
@@ -199,7 +201,13 @@ class SolverAdapter {
     T_data getErrorFromIteration() const { return errorFromIteration_; }
     T_data getErrorComputeOperator() const { return errorComputeOperator_; }
     int getNumIterationFinal() const { return numIterationFinal_; }
-    // extras (the alpaka tree has them: iterativeSolverBaseAlpaka.hpp:620-638)
+    // extras of the alpaka tree (iterativeSolverBaseAlpaka.hpp:615-638)
+    int getNumIterationPreconditionerFinal() const { return 2 * precondIterations_ * numIterationFinal_; }
+    void writeResidualHistory() const {
+        const std::vector<T_data> hst = getResidualHistory();
+        write_residual_history("residualHistory.txt", durationSolver_.count(), numIterationFinal_, getNumIterationPreconditionerFinal(),
+                               hst.data(), static_cast<int>(hst.size()), maxIteration);
+    }
     std::vector<T_data> getResidualHistory() const {
         std::vector<T_data> hst(static_cast<size_t>(numIterationFinal_) + 1);
         pps_get_history(h_, 0, hst.data(), static_cast<int>(hst.size()));
@@ -245,7 +253,7 @@ class SolverAdapter {
     const BlockGrid<DIM, T_data>& grid_;
     const ExactSolutionAndBCs<DIM, T_data>& exact_;
     const char* name_;
-    int rank_ = 0, nranksTot_ = 1;
+    int rank_ = 0, nranksTot_ = 1, precondIterations_ = 0;
     bool shared_ = false;
     pps_config cfg_{};
     pps_handle* h_ = nullptr;

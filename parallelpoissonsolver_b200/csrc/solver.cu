@@ -16,6 +16,7 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -93,6 +94,7 @@ struct pps_handle {
     int stencil_impl = 1;       // 0 plain loads, 1 TMA ring (stencil_tma.cuh)
     int by_tma = 8;             // tile rows of the TMA operator kernels (8 or 16)
     std::map<std::pair<const void*, int>, CUtensorMap> tmaps;   // key: (field, rows) main box; (field, -rows) aux box
+    std::set<const void*> smem_opt_in;   // kernels whose dynamic shared-memory limit was raised on THIS device
     int zchunk_stencil = 0, zchunk_point = 0;   // 0 = heuristic
     int lag = 3;
     std::vector<Block> blocks;
@@ -158,7 +160,6 @@ static Block* find_block(pps_handle* h, int rank) {
         if (b.g.rank == rank) return &b;
     throw std::runtime_error("block of rank " + std::to_string(rank) + " is not hosted by this handle");
 }
-static const Block* find_block(const pps_handle* h, int rank) { return find_block(const_cast<pps_handle*>(h), rank); }
 
 static cudaEvent_t pool_event(pps_handle* h) {
     if (h->event_next == h->event_pool.size()) {
@@ -280,14 +281,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
+    static EncodeTiledFn fn = [] {   // thread-safe static initialisation (rank threads of the C++ driver)
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         PPS_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
         if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled not available");
-        fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
     return fn;
 }
 
@@ -312,12 +312,10 @@ template <int BY, int STAGES, bool PAR, class Epi>
 static void launch_tma_inst(pps_handle* h, const Block& b, const double* u, const Box& box, const Epi& epi,
                             const RedCtx& red, const Tiling& t, const Ctl* ctl) {
     auto kern = stencil_tma_kernel<BY, STAGES, PAR, Epi>;
-    static bool attr_set = false;
     constexpr int smem = TmaSmem<BY, STAGES, Epi::NAUX>::kBytes;
-    if (!attr_set) {
+    // the opt-in above 48 KB is a per-device function attribute: remember it per handle (= per device), not per process
+    if (h->smem_opt_in.insert(reinterpret_cast<const void*>(kern)).second)
         PPS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
     const CUtensorMap& tm = tensor_map(h, b, u, BY, false);
     const CUtensorMap& a0 = Epi::NAUX > 0 ? tensor_map(h, b, epi.aux(0), BY, true) : tm;
     const CUtensorMap& a1 = Epi::NAUX > 1 ? tensor_map(h, b, epi.aux(1), BY, true) : tm;

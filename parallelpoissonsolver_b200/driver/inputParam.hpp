@@ -35,6 +35,18 @@ using T_Solver = BaseCG<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMa
 using T_Solver = BiCGSTAB<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, T_ActivePreconditioner>;
 #endif
 
+// result files of the reference's alpaka driver (its inputParam.hpp:46-47); -DPPS_WRITE_RESIDUAL / -DPPS_WRITE_SOLUTION
+#ifdef PPS_WRITE_RESIDUAL
+constexpr bool writeResidual = true;    // residualHistory.txt
+#else
+constexpr bool writeResidual = false;
+#endif
+#ifdef PPS_WRITE_SOLUTION
+constexpr bool writeSolution = true;    // solution.dat, raw guard-padded blocks in rank order
+#else
+constexpr bool writeSolution = false;
+#endif
+
 #ifndef PPS_NPX
 #define PPS_NPX 128
 #define PPS_NPY 128

@@ -75,6 +75,14 @@ static int rankMain(int argc, char** argv) {
     std::cout.flush();
     MPI_Barrier(MPI_COMM_WORLD);
     const auto wallEnd = std::chrono::high_resolution_clock::now();
+    // optional result files, as in the reference's alpaka driver (solverPoissonMPI_alpaka/src/main.cpp:124-146)
+    if constexpr (writeResidual) {
+        if (myRank == 0) solver.writeResidualHistory();
+    }
+    if constexpr (writeSolution) {
+        pps_compat::write_solution_block("solution.dat", myRank, blockGrid.getNtotLocalGuards(), fieldX.data());
+    }
+    MPI_Barrier(MPI_COMM_WORLD);
     if (myRank == 0) {
         std::cout << "Solver time: " << std::chrono::duration<double>(solveEnd - solveStart).count() << " seconds" << std::endl;
         std::cout << "SolverInFunction time: " << solver.getDurationSolver().count() << " seconds" << std::endl;
