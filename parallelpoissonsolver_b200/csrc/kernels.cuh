@@ -457,6 +457,36 @@ struct OpXRUpdate {
         acc[1] += (m0 ? rv.x * rv.x : 0.0) + (m1 ? rv.y * rv.y : 0.0);
     }
 };
+// fused schedule (PPS_FUSE_FULL), s lives in its own array:
+// x += alpha p + omega s ; r <- s - omega t ; acc0 += r0.r ; acc1 += r.r            (BiCGSTAB.hpp:227-246)
+template <bool PARITY>
+struct OpXRUpdateS {
+    static constexpr int NACC = 2;
+    double* x;
+    double* r;
+    const double* p;
+    const double* s;
+    const double* t;
+    const double* r0;
+    double alpha, omega;
+    __device__ __forceinline__ void begin(const Ctl* c) { alpha = c->alpha; omega = c->omega; }
+    __device__ __forceinline__ void operator()(long long idx, bool m0, bool m1, double* acc) const {
+        double2 xv = ld2(x + idx);
+        const double2 pv = ldg2(p + idx);
+        const double2 sv = ldg2(s + idx);
+        const double2 tv = ldg2(t + idx);
+        const double2 qv = ldg2(r0 + idx);
+        double2 rv;
+        xv.x = muladd<PARITY>(omega, sv.x, muladd<PARITY>(alpha, pv.x, xv.x));
+        xv.y = muladd<PARITY>(omega, sv.y, muladd<PARITY>(alpha, pv.y, xv.y));
+        rv.x = submul<PARITY>(sv.x, omega, tv.x);
+        rv.y = submul<PARITY>(sv.y, omega, tv.y);
+        st2(x + idx, xv, m0, m1);
+        st2(r + idx, rv, m0, m1);
+        acc[0] += (m0 ? qv.x * rv.x : 0.0) + (m1 ? qv.y * rv.y : 0.0);
+        acc[1] += (m0 ? rv.x * rv.x : 0.0) + (m1 ? rv.y * rv.y : 0.0);
+    }
+};
 // p <- r + beta (p - omega v)                                       (BiCGSTAB.hpp:262-272)
 template <bool PARITY>
 struct OpPUpdate {

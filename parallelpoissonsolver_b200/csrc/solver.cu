@@ -56,13 +56,15 @@ enum KernelClass : int {
     KC_DOT,
     KC_SCALAR,
     KC_APPLY,
+    KC_FUSED_P,   // p = r + beta (p - omega v), v = A p, r0.v
+    KC_FUSED_S,   // s = r - alpha v, t = A s, s.t, t.t
     KC_COUNT
 };
 static const char* kKernelNames[KC_COUNT] = {
     "stencil_dot(v=A*p, r0.v)", "s_update(r-=alpha*v)", "stencil_dot2(t=A*s, s.t, t.t)",
     "xr_update(x+=.., r-=omega*t, r0.r, r.r)", "p_update(p=r+beta*(p-omega*v))", "halo", "neumann_ghost",
     "cheb_first", "cheb_step", "residual(r=b-A*x, r.r)", "setup", "cg_apply(Ap, r.z, p.Ap)", "cg_xr", "cg_p", "dot",
-    "scalar_op", "stencil(y=A*x)"};
+    "scalar_op", "stencil(y=A*x)", "fused_p(p=r+beta*(p-omega*v), v=A*p, r0.v)", "fused_s(s=r-alpha*v, t=A*s, s.t, t.t)"};
 
 struct KernelStat {
     double ms = 0;
@@ -76,6 +78,7 @@ struct Block {
     double *mp = nullptr, *z = nullptr;              // alias p / r without a preconditioner (noneSolver.hpp:24-27)
     double *cy = nullptr, *cz = nullptr, *cw = nullptr;
     double *x_saved = nullptr, *b_saved = nullptr;
+    double *p2 = nullptr, *v2 = nullptr, *s = nullptr;   // PPS_FUSE_FULL: ping-pong p / v, separate s
     double* dudn[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* sendbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* recvbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -97,6 +100,8 @@ struct pps_handle {
     std::set<const void*> smem_opt_in;   // kernels whose dynamic shared-memory limit was raised on THIS device
     int zchunk_stencil = 0, zchunk_point = 0;   // 0 = heuristic
     int lag = 3;
+    bool fuse_full = false;     // 17-pass schedule (single block, all-Dirichlet, no preconditioner)
+    int iter_in_solve = 0;      // host-side count of enqueued iterations of the running solve
     std::vector<Block> blocks;
     cudaStream_t stream = nullptr;
     Ctl* ctl = nullptr;         // device
@@ -321,6 +326,23 @@ static void launch_tma_inst(pps_handle* h, const Block& b, const double* u, cons
     const CUtensorMap& a1 = Epi::NAUX > 1 ? tensor_map(h, b, epi.aux(1), BY, true) : tm;
     kern<<<t.grid, t.block, smem, h->launch_stream>>>(tm, a0, a1, b.g.dims, box, h->coef, t.zchunk, t.org, h->wait_next, epi, red, ctl);
     h->wait_next = HaloWait{nullptr, 0, -1, -1, 0};
+}
+
+template <int BY, int STAGES, bool PAR, class Pre, class Epi>
+static void launch_tma_pre(pps_handle* h, int kc, const Block& b, const Box& box, const Pre& pre, const Epi& epi, const RedCtx& red,
+                           const Tiling& t, bool check_done) {
+    LaunchScope ls(h, kc);
+    auto kern = stencil_tma_pre_kernel<BY, STAGES, PAR, Pre, Epi>;
+    constexpr int smem = TmaPreSmem<BY, STAGES, Pre::NIN, Epi::NAUX>::kBytes;
+    if (h->smem_opt_in.insert(reinterpret_cast<const void*>(kern)).second)
+        PPS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TmaMaps5 maps;
+    for (int q = 0; q < 3; q++) maps.in[q] = tensor_map(h, b, pre.input(q < Pre::NIN ? q : 0), BY, false);
+    for (int a = 0; a < 2; a++) maps.aux[a] = Epi::NAUX > a ? tensor_map(h, b, epi.aux(a), BY, true) : maps.in[0];
+    kern<<<t.grid, t.block, smem, h->launch_stream>>>(maps, b.g.dims, box, h->coef, t.zchunk, t.org, pre, epi, red,
+                                                       check_done ? h->ctl : nullptr);
+    check_launch(kKernelNames[kc]);
+    ls.count(1);
 }
 
 template <class Epi>
@@ -616,6 +638,7 @@ static void denormalize(pps_handle* h) {
 
 static void begin_solve(pps_handle* h) {
     h->launch_count = 0;
+    h->iter_in_solve = 0;
     for (auto& s : h->stats) { s.ms = 0; s.launches = 0; }
     h->event_next = 0;
     Ctl& c = h->ctl_host;
@@ -635,6 +658,7 @@ static void begin_solve(pps_handle* h) {
         zero_field(h, b, b.r); zero_field(h, b, b.r0); zero_field(h, b, b.p); zero_field(h, b, b.v); zero_field(h, b, b.t);
         if (b.mp != b.p) zero_field(h, b, b.mp);
         if (b.z != b.r) zero_field(h, b, b.z);
+        if (b.p2) { zero_field(h, b, b.p2); zero_field(h, b, b.v2); zero_field(h, b, b.s); }
     }
 }
 
@@ -812,6 +836,39 @@ static void bicgstab_iteration(pps_handle* h) {
     }
 }
 
+// PPS_FUSE_FULL: the same iteration in 3 kernels / 17 vector passes.  p and v are double-buffered (other CTAs still read
+// the previous p and v on their halo while this CTA stores the new ones) and s gets its own array for the same reason.
+static void bicgstab_iteration_fused(pps_handle* h) {
+    Block& b = h->blocks[0];
+    const Box box = b.g.solver_box();
+    const Tiling ts = make_tiling(h, b.g, box, true);
+    const Tiling tp = make_tiling(h, b.g, box, false);
+    if (h->iter_in_solve == 0) {
+        // first iteration: p0 = r0 is already in place (BiCGSTAB.hpp:125), plain operator
+        RedCtx red = make_red(h, 1, ts.ctas(), 0, OP_BICG_ALPHA);
+        launch_stencil(h, KC_APPLY_DOT, b, b.p, box, EpiStoreDot{b.v, b.r0}, red, ts, true);
+    } else {
+        // p' = r + beta (p - omega v) ; v' = A p' ; sum r0.v' ; alpha            :262-272 of the previous pass + :142-164
+        RedCtx red = make_red(h, 1, ts.ctas(), 0, OP_BICG_ALPHA);
+        if (h->parity) launch_tma_pre<8, 4, true>(h, KC_FUSED_P, b, box, PrePUpdate<true>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, ts, true);
+        else           launch_tma_pre<8, 4, false>(h, KC_FUSED_P, b, box, PrePUpdate<false>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, ts, true);
+        std::swap(b.p, b.p2);
+        std::swap(b.v, b.v2);
+        b.mp = b.p;
+    }
+    {   // s = r - alpha v ; t = A s ; sum s.t, t.t ; omega                        :168-225
+        RedCtx red = make_red(h, 2, ts.ctas(), 0, OP_BICG_OMEGA);
+        if (h->parity) launch_tma_pre<8, 6, true>(h, KC_FUSED_S, b, box, PreSUpdate<true>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, ts, true);
+        else           launch_tma_pre<8, 6, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, ts, true);
+    }
+    {   // x += alpha p + omega s ; r = s - omega t ; sum r0.r, r.r ; beta, rho     :227-259
+        RedCtx red = make_red(h, 2, tp.ctas(), 0, OP_BICG_RHO);
+        if (h->parity) launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdateS<true>{b.x, b.r, b.p, b.s, b.t, b.r0, 0, 0}, red, tp, true);
+        else           launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdateS<false>{b.x, b.r, b.p, b.s, b.t, b.r0, 0, 0}, red, tp, true);
+    }
+    h->iter_in_solve++;
+}
+
 static void cg_iteration(pps_handle* h) {
     const bool parity = h->parity;
     // halo(p) (no ghost reset for order 2, baseCG.hpp:123-124); Ap = A p; sum r.z, p.Ap; alpha     :118-151
@@ -887,6 +944,7 @@ static void solve(pps_handle* h) {
     }
     PPS_CUDA_CHECK(cudaEventRecord(h->ev_loop0, h->stream));
     if (cg) run_iterations(h, [&]() { cg_iteration(h); });
+    else if (h->fuse_full) run_iterations(h, [&]() { bicgstab_iteration_fused(h); });
     else    run_iterations(h, [&]() { bicgstab_iteration(h); });
     end_solve(h, /*reset_x_ghosts=*/!cg);
     PPS_CUDA_CHECK(cudaEventRecord(h->ev_end, h->stream));
@@ -961,6 +1019,15 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     if (world == 1) for (int r = 0; r < nr; r++) { Block b; b.g = make_block(cfg, r); h->blocks.push_back(std::move(b)); }
     else { Block b; b.g = make_block(cfg, rank); h->blocks.push_back(std::move(b)); }
     const bool cheb = cfg.precond == PPS_PRECOND_CHEBYSHEV;
+    {
+        // 17-pass schedule: opt-in (PPS_FUSE_FULL or PPS_FUSE=2), and only where every halo value of the fused operand can be
+        // recomputed locally: one block, no Neumann face, no preconditioner, BiCGSTAB, TMA operator kernels
+        const int want = env_int("PPS_FUSE", cfg.fusion);
+        bool neumann = false;
+        for (int f = 0; f < 6; f++) neumann = neumann || cfg.bcs_type[f] == 1;
+        h->fuse_full = want == PPS_FUSE_FULL && world == 1 && nr == 1 && !neumann && !cheb && cfg.solver == PPS_SOLVER_BICGSTAB &&
+                       h->stencil_impl == 1 && h->by_tma == 8;
+    }
     unsigned long long max_ctas = 0;
     for (auto& b : h->blocks) {
         const long long n = b.g.dims.total;
@@ -975,6 +1042,7 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
             b.z = b.r;
         }
         if (cfg.solver == PPS_SOLVER_CG && !cheb) b.z = b.r;
+        if (h->fuse_full) { b.p2 = dalloc(b, n, h->stream); b.v2 = dalloc(b, n, h->stream); b.s = dalloc(b, n, h->stream); }
         if (world > 1) {
             for (int f = 0; f < 4; f++) {
                 if (!b.g.hc[f]) continue;

@@ -193,3 +193,179 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid
 }
 
 }  // namespace pps
+
+// ================================================================================================
+// Fused operand: u = f(in0, in1, in2) is computed on the fly from NIN halo'd input streams, stored once, and
+// A u is evaluated in the same pass (PPS_FUSE_FULL: the s- and p-updates of BiCGSTAB.hpp:168-178,262-272 move into
+// the operator kernels, 19 -> 17 vector passes per iteration).  f is pointwise, so the value a thread needs at
+// its y+-1 / x-edge neighbours is recomputed from the neighbours' inputs in the ring -- bit-identical to what
+// the owner stores, no shared-memory exchange, no extra barrier.  Cells outside the solver box evaluate to 0
+// because every input is 0 there (work vectors are only ever written inside the box).
+// ================================================================================================
+namespace pps {
+
+// s = r - alpha v                                                  (BiCGSTAB.hpp:168-178)
+template <bool PARITY>
+struct PreSUpdate {
+    static constexpr int NIN = 2;
+    double* out;
+    const double* in0;   // r
+    const double* in1;   // v
+    double alpha;
+    __host__ __device__ __forceinline__ const double* input(int i) const { return i == 0 ? in0 : in1; }
+    __device__ __forceinline__ void begin(const Ctl* c) { alpha = c->alpha; }
+    __device__ __forceinline__ double f(double r, double v, double) const { return submul<PARITY>(r, alpha, v); }
+};
+// p = r + beta (p - omega v)                                        (BiCGSTAB.hpp:262-272)
+template <bool PARITY>
+struct PrePUpdate {
+    static constexpr int NIN = 3;
+    double* out;
+    const double* in0;   // r
+    const double* in1;   // p (previous)
+    const double* in2;   // v (previous)
+    double beta, omega;
+    __host__ __device__ __forceinline__ const double* input(int i) const { return i == 0 ? in0 : (i == 1 ? in1 : in2); }
+    __device__ __forceinline__ void begin(const Ctl* c) { beta = c->beta; omega = c->omega; }
+    __device__ __forceinline__ double f(double r, double p, double v) const { return muladd<PARITY>(beta, submul<PARITY>(p, omega, v), r); }
+};
+
+template <int BY, int STAGES, int NIN, int NAUX>
+struct TmaPreSmem {
+    static constexpr int kMainElems = kTmaBoxX * (BY + 2);
+    static constexpr int kAuxElems = 64 * BY;
+    static constexpr int kStageElems = NIN * kMainElems + NAUX * kAuxElems;
+    static constexpr int kMainBytes = NIN * kMainElems * 8;
+    static constexpr int kStageBytes = kStageElems * 8;
+    static constexpr int kBytes = STAGES * kStageBytes + 2 * STAGES * 8;
+};
+
+struct TmaMaps5 {
+    CUtensorMap in[3];
+    CUtensorMap aux[2];
+};
+
+template <int BY, int STAGES, bool PARITY, class Pre, class Epi>
+__global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_pre_kernel(const __grid_constant__ TmaMaps5 maps, Dims d, Box rg, Coef cf,
+                                                                       int zchunk, TileOrigin org, Pre pre, Epi epi, RedCtx red,
+                                                                       const Ctl* ctl) {
+    if (ctl != nullptr && ctl->done) return;
+    constexpr int NACC = Epi::NACC;
+    constexpr int NAUX = Epi::NAUX;
+    constexpr int NIN = Pre::NIN;
+    constexpr int SX = kTmaBoxX;
+    using SM = TmaPreSmem<BY, STAGES, NIN, NAUX>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * SM::kStageBytes);
+    uint64_t* empty = full + STAGES;
+
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int col0 = kFirstDataCol + 64 * (blockIdx.x + org.bx0);
+    const int y0 = 1 + BY * (blockIdx.y + org.by0);
+    const int kchunk = org.kfirst + blockIdx.z * zchunk;
+    const int kb = max(rg.k0, kchunk), ke = min(rg.k1, kchunk + zchunk);
+    const int nplanes = ke - kb + 2;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], BY);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double acc[NACC > 0 ? NACC : 1];
+#pragma unroll
+    for (int a = 0; a < (NACC > 0 ? NACC : 1); a++) acc[a] = 0.0;
+
+    if (kb < ke) {
+        if (warp == BY) {
+            if (lane == 0) {
+                for (int p = 0; p < nplanes; p++) {
+                    const int s = p % STAGES;
+                    if (p >= STAGES) mbar_wait(&empty[s], ((p / STAGES) - 1) & 1);
+                    double* dst = ring + s * SM::kStageElems;
+                    const bool with_aux = NAUX > 0 && p >= 1 && p <= nplanes - 2;
+                    const int kk = kb - 1 + p;
+                    mbar_arrive_expect_tx(&full[s], with_aux ? SM::kStageBytes : SM::kMainBytes);
+#pragma unroll
+                    for (int q = 0; q < NIN; q++)
+                        tma_load_3d(dst + q * SM::kMainElems, &maps.in[q], &full[s], col0 - kTmaLead, y0 - 1, kk);
+                    if (with_aux) {
+#pragma unroll
+                        for (int a = 0; a < NAUX; a++)
+                            tma_load_3d(dst + NIN * SM::kMainElems + a * SM::kAuxElems, &maps.aux[a], &full[s], col0, y0, kk);
+                    }
+                }
+            }
+        } else {
+            pre.begin(ctl);
+            const int col = col0 + 2 * lane;
+            const int j = y0 + warp;
+            const int i0 = col - kOff;
+            const bool jr = j >= rg.j0 && j < rg.j1;
+            const bool m0 = jr && i0 >= rg.i0 && i0 < rg.i1;
+            const bool m1 = jr && i0 + 1 >= rg.i0 && i0 + 1 < rg.i1;
+            const bool warp_any = __any_sync(kFullMask, m0 || m1);
+            const long long colc = col < d.pitch ? col : d.pitch - 2;
+            const long long rowoff = colc + d.pitch * min(j, d.ny);
+            const int so = (warp + 1) * SX + kTmaLead + 2 * lane;
+            const int sa = NIN * SM::kMainElems + warp * 64 + 2 * lane;
+
+            // u at two adjacent cells / one cell, from the inputs of ring stage `stg`
+            auto eval2 = [&](const double* stg, int off) {
+                const double2 a = *reinterpret_cast<const double2*>(stg + off);
+                double2 b = make_double2(0.0, 0.0), c = make_double2(0.0, 0.0);
+                if (NIN > 1) b = *reinterpret_cast<const double2*>(stg + SM::kMainElems + off);
+                if (NIN > 2) c = *reinterpret_cast<const double2*>(stg + 2 * SM::kMainElems + off);
+                return make_double2(pre.f(a.x, b.x, c.x), pre.f(a.y, b.y, c.y));
+            };
+            auto eval1 = [&](const double* stg, int off) {
+                const double a = stg[off];
+                const double b = NIN > 1 ? stg[SM::kMainElems + off] : 0.0;
+                const double c = NIN > 2 ? stg[2 * SM::kMainElems + off] : 0.0;
+                return pre.f(a, b, c);
+            };
+
+            mbar_wait(&full[0], 0);
+            double2 cm = eval2(ring, so);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[0]);
+            mbar_wait(&full[1 % STAGES], (1 / STAGES) & 1);
+            double2 cc = eval2(ring + (1 % STAGES) * SM::kStageElems, so);
+            for (int k = kb; k < ke; ++k) {
+                const int p = k - kb + 1;
+                const int s = p % STAGES, sn = (p + 1) % STAGES;
+                mbar_wait(&full[sn], ((p + 1) / STAGES) & 1);
+                const double* stg = ring + s * SM::kStageElems;
+                const double2 cp = eval2(ring + sn * SM::kStageElems, so);
+                if (warp_any) {
+                    const double2 ym = eval2(stg, so - SX);
+                    const double2 yp = eval2(stg, so + SX);
+                    double2 ax[NAUX > 0 ? NAUX : 1];
+#pragma unroll
+                    for (int a = 0; a < NAUX; a++) ax[a] = *reinterpret_cast<const double2*>(stg + sa + a * SM::kAuxElems);
+                    double xl = __shfl_up_sync(kFullMask, cc.y, 1);
+                    double xr = __shfl_down_sync(kFullMask, cc.x, 1);
+                    if (lane == 0) xl = eval1(stg, so - 1);
+                    if (lane == 31) xr = eval1(stg, so + 2);
+                    double2 au;
+                    au.x = laplacian<PARITY>(cf, xl, cc.x, cc.y, ym.x, yp.x, cm.x, cp.x);
+                    au.y = laplacian<PARITY>(cf, cc.x, cc.y, xr, ym.y, yp.y, cm.y, cp.y);
+                    const long long idx = rowoff + k * d.plane;
+                    st2(pre.out + idx, cc, m0, m1);
+                    epi(idx, au, cc, ax, m0, m1, acc);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                cm = cc;
+                cc = cp;
+            }
+        }
+    }
+    if (NACC > 0) grid_reduce_finish<(NACC > 0 ? NACC : 1)>(acc, red);
+}
+
+}  // namespace pps
