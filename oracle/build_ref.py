@@ -128,7 +128,10 @@ def build_dropin(name, force=False):
     if not os.path.exists(os.path.join(lib_dir, "libpps_b200.so")):
         return ""
     exe = os.path.join(OUT, "bin", "ref_main_on_b200_" + name)
-    if not force and os.path.exists(exe):
+    compat = os.path.join(root, "include", "reference_compat")
+    deps = [os.path.join(compat, f) for f in os.listdir(compat)] + [os.path.join(root, "include", "pps_b200.h"),
+            os.path.join(root, "parallelpoissonsolver_b200", "driver", "ref_main_launcher.cpp")]
+    if not force and os.path.exists(exe) and all(os.path.getmtime(d) <= os.path.getmtime(exe) for d in deps):
         return exe
     cfgdir = make_cfg_dir(name, CONFIGS[name])
     only = os.path.join(cfgdir, "config_only")
