@@ -40,6 +40,10 @@ CASES = [
     ("d64_t12", (1, 1, 1), False), ("d64_t12", (1, 1, 2), False), ("d64_t12", (2, 2, 2), False),
     ("d64_cheb", (1, 1, 1), False),
     ("default", (1, 1, 1), False), ("default", (1, 1, 2), False), ("default", (2, 1, 1), False), ("default", (2, 2, 2), False),
+    # layouts with MIDDLE ranks (neighbours on both sides of an axis)
+    ("d32", (1, 1, 4), False), ("d32", (4, 1, 1), False), ("d32_cheb", (1, 4, 1), False), ("d32_cheb", (1, 1, 4), True),
+    ("m24", (3, 1, 1), False), ("m24", (1, 1, 4), False), ("m24_cheb", (3, 2, 1), False), ("m24_cheb", (1, 1, 4), False),
+    ("cg32", (1, 1, 4), False), ("cg32_cheb", (4, 2, 1), False), ("d64", (1, 1, 8), False), ("d64_cheb", (1, 1, 8), False),
 ]
 
 

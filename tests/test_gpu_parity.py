@@ -179,7 +179,10 @@ def test_virtual_ranks_match_the_same_rank_layout(nranks, precond):
 
 GOLDEN_GPU = ["d16_111", "d16_222", "d32_111", "d32_112", "d32_cheb_111", "d32_cheb_222", "m24_111", "m24_222",
               "m24_cheb_111", "m24_cheb_112", "m24_cheb_221", "n24_111", "n24_212", "cg32_111", "cg32_122",
-              "cg32_cheb_111", "cg32_cheb_211", "m32_cheb_112", "d64_111", "d64_222", "d64_cheb_111"]
+              "cg32_cheb_111", "cg32_cheb_211", "m32_cheb_112", "d64_111", "d64_222", "d64_cheb_111",
+              # layouts with middle blocks (neighbours on both sides of an axis)
+              "d32_114", "d32_411", "d32_cheb_114", "d32_cheb_141", "m24_311", "m24_114", "m24_cheb_321", "m24_cheb_114",
+              "cg32_114", "cg32_cheb_421"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)
