@@ -336,10 +336,12 @@ static void launch_tma_pre(pps_handle* h, int kc, const Block& b, const Box& box
     constexpr int smem = TmaPreSmem<BY, STAGES, Pre::NIN, Epi::NAUX>::kBytes;
     if (h->smem_opt_in.insert(reinterpret_cast<const void*>(kern)).second)
         PPS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    TmaMaps5 maps;
-    for (int q = 0; q < 3; q++) maps.in[q] = tensor_map(h, b, pre.input(q < Pre::NIN ? q : 0), BY, false);
-    for (int a = 0; a < 2; a++) maps.aux[a] = Epi::NAUX > a ? tensor_map(h, b, epi.aux(a), BY, true) : maps.in[0];
-    kern<<<t.grid, t.block, smem, h->launch_stream>>>(maps, b.g.dims, box, h->coef, t.zchunk, t.org, pre, epi, red,
+    const CUtensorMap& i0 = tensor_map(h, b, pre.input(0), BY, false);
+    const CUtensorMap& i1 = Pre::NIN > 1 ? tensor_map(h, b, pre.input(1), BY, false) : i0;
+    const CUtensorMap& i2 = Pre::NIN > 2 ? tensor_map(h, b, pre.input(2), BY, false) : i0;
+    const CUtensorMap& a0 = Epi::NAUX > 0 ? tensor_map(h, b, epi.aux(0), BY, true) : i0;
+    const CUtensorMap& a1 = Epi::NAUX > 1 ? tensor_map(h, b, epi.aux(1), BY, true) : i0;
+    kern<<<t.grid, t.block, smem, h->launch_stream>>>(i0, i1, i2, a0, a1, b.g.dims, box, h->coef, t.zchunk, t.org, pre, epi, red,
                                                        check_done ? h->ctl : nullptr);
     check_launch(kKernelNames[kc]);
     ls.count(1);

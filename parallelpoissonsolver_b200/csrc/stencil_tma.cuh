@@ -240,15 +240,16 @@ struct TmaPreSmem {
     static constexpr int kBytes = STAGES * kStageBytes + 2 * STAGES * 8;
 };
 
-struct TmaMaps5 {
-    CUtensorMap in[3];
-    CUtensorMap aux[2];
-};
-
+// The tensor maps are individual __grid_constant__ parameters, exactly like in stencil_tma_kernel (whose maps also change
+// from launch to launch, e.g. the rotating Chebyshev buffers), not members of a wrapper struct.
 template <int BY, int STAGES, bool PARITY, class Pre, class Epi>
-__global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_pre_kernel(const __grid_constant__ TmaMaps5 maps, Dims d, Box rg, Coef cf,
-                                                                       int zchunk, TileOrigin org, Pre pre, Epi epi, RedCtx red,
-                                                                       const Ctl* ctl) {
+__global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_pre_kernel(const __grid_constant__ CUtensorMap map_in0,
+                                                                       const __grid_constant__ CUtensorMap map_in1,
+                                                                       const __grid_constant__ CUtensorMap map_in2,
+                                                                       const __grid_constant__ CUtensorMap map_aux0,
+                                                                       const __grid_constant__ CUtensorMap map_aux1, Dims d, Box rg,
+                                                                       Coef cf, int zchunk, TileOrigin org, Pre pre, Epi epi,
+                                                                       RedCtx red, const Ctl* ctl) {
     if (ctl != nullptr && ctl->done) return;
     constexpr int NACC = Epi::NACC;
     constexpr int NAUX = Epi::NAUX;
@@ -290,13 +291,12 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_pre_kernel(const __
                     const bool with_aux = NAUX > 0 && p >= 1 && p <= nplanes - 2;
                     const int kk = kb - 1 + p;
                     mbar_arrive_expect_tx(&full[s], with_aux ? SM::kStageBytes : SM::kMainBytes);
-#pragma unroll
-                    for (int q = 0; q < NIN; q++)
-                        tma_load_3d(dst + q * SM::kMainElems, &maps.in[q], &full[s], col0 - kTmaLead, y0 - 1, kk);
+                    tma_load_3d(dst, &map_in0, &full[s], col0 - kTmaLead, y0 - 1, kk);
+                    if (NIN > 1) tma_load_3d(dst + SM::kMainElems, &map_in1, &full[s], col0 - kTmaLead, y0 - 1, kk);
+                    if (NIN > 2) tma_load_3d(dst + 2 * SM::kMainElems, &map_in2, &full[s], col0 - kTmaLead, y0 - 1, kk);
                     if (with_aux) {
-#pragma unroll
-                        for (int a = 0; a < NAUX; a++)
-                            tma_load_3d(dst + NIN * SM::kMainElems + a * SM::kAuxElems, &maps.aux[a], &full[s], col0, y0, kk);
+                        if (NAUX > 0) tma_load_3d(dst + NIN * SM::kMainElems, &map_aux0, &full[s], col0, y0, kk);
+                        if (NAUX > 1) tma_load_3d(dst + NIN * SM::kMainElems + SM::kAuxElems, &map_aux1, &full[s], col0, y0, kk);
                     }
                 }
             }
