@@ -279,6 +279,22 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+def arm_watchdog(seconds, rank):
+    """A stalled collective must never hold a GPU box until an outer limit kills it: after `seconds` the process
+    exits hard (the launcher then tears the other ranks down)."""
+    if seconds <= 0:
+        return None
+
+    def fire():
+        print(f"[bench] watchdog: rank {rank} made no JSON line within {seconds} s -- aborting", file=sys.stderr, flush=True)
+        os._exit(3)
+
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def progress(rank, msg):
     """timestamped marker on stderr (rank 0): localises a stall without touching the JSON line on stdout"""
     if rank == 0:
@@ -296,6 +312,7 @@ def main():
     ap.add_argument("--max-iter", type=int, default=6000)
     ap.add_argument("--warmup-iters", type=int, default=100, help="iteration cap of the warm-up solves when N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=1500, help="hard exit after this many seconds (0 = off)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -304,6 +321,7 @@ def main():
     npglobal = parse_workload(args.workload, max(args.gpus, world))
 
     protect_stdout()
+    arm_watchdog(args.watchdog, rank)
     if args.impl == "reference":
         reference_arm(args, npglobal, rank)
         return

@@ -29,6 +29,10 @@ def main():
     flags = sys.argv[4:]
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     assert px * py * pz == world
+    import threading
+    wd = threading.Timer(240, lambda: os._exit(3))   # never hold a GPU box on a stalled collective
+    wd.daemon = True
+    wd.start()
     backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
         torch.cuda.set_device(local)
