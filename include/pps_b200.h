@@ -71,8 +71,13 @@ typedef struct pps_config {
     int arithmetic;           /* PPS_ARITH_* */
     int fusion;               /* PPS_FUSE_* */
     int device;               /* CUDA device ordinal, -1 = current */
-    int reserved[8];
+    int flags;                /* PPS_FLAG_* */
+    int reserved[7];
 } pps_config;
+
+/* pps_config.flags */
+#define PPS_FLAG_OPERATOR_ONLY 1   /* allocate only what pps_bench_operator / pps_apply_operator need (3 vectors instead of 7+):
+                                      the operator-apply bandwidth sweep up to the largest grid that fits the GPU; pps_solve fails */
 
 typedef struct pps_block_info {   /* BlockGrid getters, blockGrid.hpp:40-145 */
     int rank;
@@ -145,7 +150,9 @@ int pps_check_solution(pps_handle* h, int rank, const double* u_exact_host, doub
 int pps_apply_operator(pps_handle* h, int rank, const double* in_host, double* out_host);
 /* X = M(B) for every local block (T_Preconditioner::operator(), chebyshevIteration.hpp:48-140) */
 int pps_apply_preconditioner(pps_handle* h, int rank, const double* b_host, double* x_host);
-/* device-resident timing of `reps` operator applies on block 0's work vectors; returns average ms */
+/* device-resident timing of `reps` operator applies on block 0's work vectors; returns average ms.
+ * with_dot: 0 y = A x; 1 fused with sum(w.y); bit 1 (value 2 or 3): every apply is preceded by the face halo exchange
+ * of x with the neighbouring ranks (world_size > 1: the weak-scaling leg of the sweep) */
 int pps_bench_operator(pps_handle* h, int reps, int with_dot, double* avg_ms);
 /* average device time (ms) per launch of kernel class `which` during the last pps_solve, measured with
  * CUDA events on the launching stream when profiling is enabled: pps_set_profiling(h, 1) brackets every kernel

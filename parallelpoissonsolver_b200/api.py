@@ -11,6 +11,7 @@ SOLVER_BICGSTAB, SOLVER_CG = 0, 1
 PRECOND_NONE, PRECOND_CHEBYSHEV = 0, 1
 ARITH_FAST, ARITH_PARITY = 0, 1
 FUSE_AUTO, FUSE_SPLIT, FUSE_FULL = 0, 1, 2
+FLAG_OPERATOR_ONLY = 1
 ABI_VERSION = 1
 UNIQUE_ID_BYTES = 128
 
@@ -28,7 +29,7 @@ class Config(C.Structure):
         ("solver", C.c_int), ("precond", C.c_int), ("tolerance", C.c_double), ("max_iter", C.c_int),
         ("cheb_max_iter", C.c_int), ("cheb_epsilon", C.c_double), ("cheb_rescale_min", C.c_double),
         ("cheb_rescale_max", C.c_double), ("order_neumann", C.c_int), ("arithmetic", C.c_int), ("fusion", C.c_int),
-        ("device", C.c_int), ("reserved", C.c_int * 8),
+        ("device", C.c_int), ("flags", C.c_int), ("reserved", C.c_int * 7),
     ]
 
 
@@ -107,7 +108,7 @@ def default_config() -> Config:
 def make_config(npglobal, nranks=(1, 1, 1), ds=(0.1, 0.1, 0.1), origin=(0.0, 0.0, 0.0), bcs=(0, 0, 0, 0, 0, 0),
                 solver=SOLVER_BICGSTAB, precond=PRECOND_NONE, tolerance=1e-8, max_iter=1700, cheb_max_iter=11,
                 cheb_epsilon=1e-4, cheb_rescale_min=500.0, cheb_rescale_max=1 - 1e-4, arithmetic=ARITH_FAST,
-                fusion=FUSE_AUTO, device=-1) -> Config:
+                fusion=FUSE_AUTO, device=-1, flags=0) -> Config:
     c = Config()
     c.abi_version = ABI_VERSION
     c.dim = 3
@@ -123,6 +124,7 @@ def make_config(npglobal, nranks=(1, 1, 1), ds=(0.1, 0.1, 0.1), origin=(0.0, 0.0
     c.cheb_rescale_min, c.cheb_rescale_max = float(cheb_rescale_min), float(cheb_rescale_max)
     c.order_neumann = 2
     c.arithmetic, c.fusion, c.device = arithmetic, fusion, device
+    c.flags = flags
     return c
 
 
@@ -276,9 +278,9 @@ class PoissonSolver:
         self._ck(self.L.pps_apply_preconditioner(self.h, rank, _ptr(field), _ptr(out)))
         return out
 
-    def bench_operator(self, reps: int = 20, with_dot: bool = False) -> float:
+    def bench_operator(self, reps: int = 20, with_dot: bool = False, with_halo: bool = False) -> float:
         ms = C.c_double()
-        self._ck(self.L.pps_bench_operator(self.h, reps, int(with_dot), C.byref(ms)))
+        self._ck(self.L.pps_bench_operator(self.h, reps, int(with_dot) | (2 if with_halo else 0), C.byref(ms)))
         return ms.value
 
     def set_profiling(self, on: bool):

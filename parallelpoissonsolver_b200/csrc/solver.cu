@@ -100,6 +100,7 @@ struct pps_handle {
     std::set<const void*> smem_opt_in;   // kernels whose dynamic shared-memory limit was raised on THIS device
     int zchunk_stencil = 0, zchunk_point = 0;   // 0 = heuristic
     int lag = 3;
+    bool operator_only = false; // PPS_FLAG_OPERATOR_ONLY: only p, v, r0 exist
     bool fuse_full = false;     // 17-pass schedule (single block, all-Dirichlet, no preconditioner)
     int iter_in_solve = 0;      // host-side count of enqueued iterations of the running solve
     std::vector<Block> blocks;
@@ -915,6 +916,7 @@ static void cg_iteration(pps_handle* h) {
 }
 
 static void solve(pps_handle* h) {
+    if (h->operator_only) throw std::runtime_error("this handle was created with PPS_FLAG_OPERATOR_ONLY: no solver vectors");
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
     const auto wall0 = std::chrono::high_resolution_clock::now();
     PPS_CUDA_CHECK(cudaEventRecord(h->ev_start, h->stream));
@@ -1031,8 +1033,16 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
                        h->stencil_impl == 1 && h->by_tma == 8;
     }
     unsigned long long max_ctas = 0;
+    h->operator_only = (cfg.flags & PPS_FLAG_OPERATOR_ONLY) != 0;
+    if (h->operator_only) h->fuse_full = false;
     for (auto& b : h->blocks) {
         const long long n = b.g.dims.total;
+        if (h->operator_only) {
+            b.p = dalloc(b, n, h->stream); b.v = dalloc(b, n, h->stream); b.r0 = dalloc(b, n, h->stream);
+            b.mp = b.p;
+            max_ctas += static_cast<unsigned long long>((b.g.n[0] + 63) / 64) * ((b.g.n[1] + 3) / 4) * b.g.n[2];
+            continue;
+        }
         b.x = dalloc(b, n, h->stream); b.b = dalloc(b, n, h->stream); b.r = dalloc(b, n, h->stream);
         b.r0 = dalloc(b, n, h->stream); b.p = dalloc(b, n, h->stream); b.v = dalloc(b, n, h->stream);
         b.t = dalloc(b, n, h->stream);
@@ -1245,6 +1255,7 @@ int pps_eigenvalues(const pps_handle* h, int rank, double g[2], double l[2]) {
 
 int pps_set_fields(pps_handle* h, int rank, const double* x_host, const double* b_host) {
     PPS_API_BEGIN
+    if (h->operator_only) throw std::runtime_error("pps_set_fields: handle is operator-only (PPS_FLAG_OPERATOR_ONLY)");
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
     Block* b = find_block(h, rank);
     if (x_host) upload_field(h, *b, b->x, x_host);
@@ -1276,6 +1287,7 @@ int pps_solve(pps_handle* h) {
 
 int pps_save_fields(pps_handle* h) {
     PPS_API_BEGIN
+    if (h->operator_only) throw std::runtime_error("pps_save_fields: handle is operator-only (PPS_FLAG_OPERATOR_ONLY)");
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
     for (auto& b : h->blocks) {
         if (!b.x_saved) { b.x_saved = dalloc(b, b.g.dims.total, h->stream); b.b_saved = dalloc(b, b.g.dims.total, h->stream); }
@@ -1288,6 +1300,7 @@ int pps_save_fields(pps_handle* h) {
 
 int pps_restore_fields(pps_handle* h) {
     PPS_API_BEGIN
+    if (h->operator_only) throw std::runtime_error("pps_restore_fields: handle is operator-only (PPS_FLAG_OPERATOR_ONLY)");
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
     for (auto& b : h->blocks) {
         if (!b.x_saved) throw std::runtime_error("pps_restore_fields without pps_save_fields");
@@ -1300,6 +1313,7 @@ int pps_restore_fields(pps_handle* h) {
 
 int pps_get_solution(pps_handle* h, int rank, double* x_host) {
     PPS_API_BEGIN
+    if (h->operator_only) throw std::runtime_error("pps_get_solution: handle is operator-only (PPS_FLAG_OPERATOR_ONLY)");
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
     Block* b = find_block(h, rank);
     download_field(h, *b, x_host, b->x);
@@ -1309,6 +1323,7 @@ int pps_get_solution(pps_handle* h, int rank, double* x_host) {
 
 int pps_get_rhs(pps_handle* h, int rank, double* b_host) {
     PPS_API_BEGIN
+    if (h->operator_only) throw std::runtime_error("pps_get_rhs: handle is operator-only (PPS_FLAG_OPERATOR_ONLY)");
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
     Block* b = find_block(h, rank);
     download_field(h, *b, b_host, b->b);
@@ -1334,6 +1349,7 @@ int pps_get_history(const pps_handle* h, int which, double* out, int capacity) {
 
 int pps_check_solution(pps_handle* h, int rank, const double* u_exact_host, double* sum_abs, double* max_abs) {
     PPS_API_BEGIN
+    if (h->operator_only) throw std::runtime_error("pps_check_solution: handle is operator-only (PPS_FLAG_OPERATOR_ONLY)");
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
     Block* b = find_block(h, rank);
     std::vector<double> x(static_cast<size_t>(b->g.ref_total()));
@@ -1371,6 +1387,7 @@ int pps_apply_operator(pps_handle* h, int rank, const double* in_host, double* o
 
 int pps_apply_preconditioner(pps_handle* h, int rank, const double* b_host, double* x_host) {
     PPS_API_BEGIN
+    if (h->operator_only) throw std::runtime_error("pps_apply_preconditioner: handle is operator-only (PPS_FLAG_OPERATOR_ONLY)");
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
     Block* b = find_block(h, rank);
     upload_field(h, *b, b->p, b_host);
@@ -1394,7 +1411,10 @@ int pps_bench_operator(pps_handle* h, int reps, int with_dot, double* avg_ms) {
     upload_ctl(h);
     PPS_CUDA_CHECK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), h->stream));
     const int saved_world = h->world;
+    const bool with_halo = (with_dot & 2) != 0;
+    with_dot &= 1;
     auto once = [&]() {
+        if (with_halo) halo_exchange(h, sel_p, false);
         if (with_dot) {
             RedCtx red = make_red(h, 1, t.ctas(), 0, OP_NONE);
             red.op = OP_NONE;
