@@ -646,6 +646,20 @@ __global__ void face_copy_kernel(double* __restrict__ dst, const double* __restr
     }
 }
 
+// peer-memory halo path: publish / await the epoch of an exchange through a flag in (peer) device memory
+__global__ void publish_epoch_sys_kernel(unsigned int* flag, unsigned int epoch) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+__global__ void await_epoch_sys_kernel(const unsigned int* flag, unsigned int epoch) {
+    unsigned int v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (static_cast<int>(v - epoch) >= 0) break;
+        __nanosleep(100);
+    } while (true);
+}
+
 // pack / unpack a face into / from a contiguous buffer (NCCL send/recv of x- and y-faces)
 __global__ void face_pack_kernel(double* __restrict__ buf, const double* __restrict__ f, FaceGeom g, const Ctl* ctl,
                                  int ignore_done) {

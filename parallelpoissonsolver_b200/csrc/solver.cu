@@ -7,6 +7,7 @@
 // after the NCCL allreduce; the host only reads the residual history (host-mapped) a few iterations late to
 // decide when to stop launching, and every kernel returns at once after the device has set `done`.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -125,6 +126,13 @@ struct pps_handle {
     unsigned int halo_epoch = 0;
     HaloWait wait_next{nullptr, 0, -1, -1, 0};   // consumed by the next TMA operator launch
     int debug_no_halo = 0;            // timing experiments only: skip the exchange (wrong results)
+    // peer-memory halo path (PPS_HALO_P2P=1, z-slabs): neighbours' field / flag arrays mapped through CUDA IPC
+    bool p2p = false;
+    double* peer_field[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [lo/hi neighbour][0 = Mp, 1 = z]
+    unsigned int* peer_flags[2] = {nullptr, nullptr};                      // neighbour's recv_epoch array
+    unsigned int* recv_epoch = nullptr;                                    // mine: [field][face lo/hi], written by the neighbours
+    unsigned int field_epoch[2] = {0, 0};
+    std::vector<void*> ipc_opened;
     Coef coef{};
     // Chebyshev constants (chebyshevIteration.hpp:22-26)
     double theta = 0, delta = 0, sigma = 0;
@@ -479,6 +487,92 @@ static void halo_exchange(pps_handle* h, FieldSel sel, bool check_done, bool on_
     check_launch("halo");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Peer-memory halo path for z-slabs (opt-in, PPS_HALO_P2P=1).  An exchange of field f is, per neighbour, one
+// copy-engine cudaMemcpyAsync of my boundary data plane straight into the neighbour's guard plane followed by a
+// one-thread st.release.sys of the exchange epoch into the neighbour's flag; the consumer side waits for its own
+// flags with a one-thread kernel on the boundary stream.  No NCCL kernel runs on the SMs and no packing is needed
+// (a z-plane of the pitched layout is contiguous).  Re-use of a guard plane is safe without a credit message: two
+// exchanges of the same field are always separated by the scalar allreduces of the iteration, which every rank
+// only passes after its operator launches that read the previous content have completed.
+// ------------------------------------------------------------------------------------------------
+struct PeerInfo {
+    long long pid;
+    int device;
+    int pad;
+    cudaIpcMemHandle_t mp, z, flags;
+    unsigned long long raw_mp, raw_z, raw_flags;
+};
+
+static void setup_p2p(pps_handle* h) {
+    Block& b = h->blocks[0];
+    for (int f = 0; f < 4; f++)
+        if (b.g.hc[f]) return;   // x / y faces would need packing: NCCL path
+    if (!(b.g.hc[4] || b.g.hc[5]) || h->cfg.solver != PPS_SOLVER_BICGSTAB) return;
+    PPS_CUDA_CHECK(cudaMalloc(&h->recv_epoch, 4 * sizeof(unsigned int)));
+    PPS_CUDA_CHECK(cudaMemsetAsync(h->recv_epoch, 0, 4 * sizeof(unsigned int), h->stream));
+    PeerInfo mine{};
+    mine.pid = static_cast<long long>(getpid());
+    mine.device = h->device;
+    PPS_CUDA_CHECK(cudaIpcGetMemHandle(&mine.mp, b.mp));
+    PPS_CUDA_CHECK(cudaIpcGetMemHandle(&mine.z, b.z));
+    PPS_CUDA_CHECK(cudaIpcGetMemHandle(&mine.flags, h->recv_epoch));
+    mine.raw_mp = reinterpret_cast<unsigned long long>(b.mp);
+    mine.raw_z = reinterpret_cast<unsigned long long>(b.z);
+    mine.raw_flags = reinterpret_cast<unsigned long long>(h->recv_epoch);
+    const size_t sz = sizeof(PeerInfo);
+    if (sz * h->world > sizeof(double) * kMaxAcc * static_cast<size_t>(h->partial_capacity)) return;
+    char* scratch = reinterpret_cast<char*>(h->partials);
+    PPS_CUDA_CHECK(cudaMemcpyAsync(scratch + sz * h->rank, &mine, sz, cudaMemcpyHostToDevice, h->stream));
+    PPS_NCCL_CHECK(nccl().AllGather(scratch + sz * h->rank, scratch, sz, ncclChar, h->comm, h->stream));
+    std::vector<PeerInfo> all(h->world);
+    PPS_CUDA_CHECK(cudaMemcpyAsync(all.data(), scratch, sz * h->world, cudaMemcpyDeviceToHost, h->stream));
+    PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int up = 0; up < 2; up++) {
+        if (!b.g.hc[4 + up]) continue;
+        const PeerInfo& pi = all[b.g.nbr[4 + up]];
+        if (pi.pid == mine.pid) {
+            // rank-threads of one process (C++ driver): plain peer access
+            if (pi.device != h->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(pi.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PPS_CUDA_CHECK(e);
+                cudaGetLastError();
+            }
+            h->peer_field[up][0] = reinterpret_cast<double*>(pi.raw_mp);
+            h->peer_field[up][1] = reinterpret_cast<double*>(pi.raw_z);
+            h->peer_flags[up] = reinterpret_cast<unsigned int*>(pi.raw_flags);
+        } else {
+            void* q = nullptr;
+            PPS_CUDA_CHECK(cudaIpcOpenMemHandle(&q, pi.mp, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_field[up][0] = static_cast<double*>(q); h->ipc_opened.push_back(q);
+            PPS_CUDA_CHECK(cudaIpcOpenMemHandle(&q, pi.z, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_field[up][1] = static_cast<double*>(q); h->ipc_opened.push_back(q);
+            PPS_CUDA_CHECK(cudaIpcOpenMemHandle(&q, pi.flags, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_flags[up] = static_cast<unsigned int*>(q); h->ipc_opened.push_back(q);
+        }
+    }
+    h->p2p = true;
+}
+
+// push my boundary planes of field `fidx` (0 = Mp, 1 = z) into the neighbours' guard planes on the halo stream
+static unsigned int halo_push_p2p(pps_handle* h, int fidx, double* fld) {
+    Block& b = h->blocks[0];
+    const unsigned int epoch = ++h->field_epoch[fidx];
+    LaunchScope ls(h, KC_HALO);
+    for (int up = 0; up < 2; up++) {
+        if (!b.g.hc[4 + up]) continue;
+        const long long kdata = up ? b.g.n[2] : 1;                 // my boundary data plane
+        const long long kguard = up ? 0 : b.g.n[2] + 1;            // the neighbour's guard plane that faces me
+        PPS_CUDA_CHECK(cudaMemcpyAsync(h->peer_field[up][fidx] + kguard * b.g.dims.plane, fld + kdata * b.g.dims.plane,
+                                       sizeof(double) * static_cast<size_t>(b.g.dims.plane), cudaMemcpyDefault, h->halo_stream));
+        // my upper neighbour receives on ITS lower face (slot 0), my lower neighbour on its upper face (slot 1)
+        publish_epoch_sys_kernel<<<1, 1, 0, h->halo_stream>>>(h->peer_flags[up] + 2 * fidx + (up ? 0 : 1), epoch);
+        ls.count(1);
+    }
+    check_launch("halo_push_p2p");
+    return epoch;
+}
+
 // resetNeumanBCs<isMainLoop, fieldData> (iterativeSolverBase.hpp:62-169)
 static void neumann_ghosts(pps_handle* h, Block& b, double* field, bool with_value, bool check_done) {
     bool any = false;
@@ -744,11 +838,15 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
         Block& b = h->blocks[0];
         PPS_CUDA_CHECK(cudaEventRecord(h->ev_field_ready, h->stream));
         PPS_CUDA_CHECK(cudaStreamWaitEvent(h->halo_stream, h->ev_field_ready, 0));
-        halo_exchange(h, sel, true, /*on_halo_stream=*/true);
+        const bool use_p2p = h->p2p && (sel == sel_mp || sel == sel_z);
+        unsigned int p2p_epoch = 0;
+        const int p2p_field = sel == sel_z ? 1 : 0;
+        if (use_p2p) p2p_epoch = halo_push_p2p(h, p2p_field, sel(b));
+        else halo_exchange(h, sel, true, /*on_halo_stream=*/true);
         const bool z_only = !(b.g.hc[0] || b.g.hc[1] || b.g.hc[2] || b.g.hc[3]);
         if (ghosts) neumann_ghosts(h, b, sel(b), false, true);
         const Tiling t_all = make_tiling(h, b.g, b.g.solver_box(), true);
-        if (z_only && h->stencil_impl == 1 && h->overlap == 2 && t_all.grid.z >= 3) {
+        if (!use_p2p && z_only && h->stencil_impl == 1 && h->overlap == 2 && t_all.grid.z >= 3) {
             // EXPERIMENTAL (PPS_OVERLAP=2): ONE launch; the first / last z-chunk run last and their TMA producer waits in-kernel
             // for the faces.  Fastest when it works, but it needs the NCCL kernel to become resident while waiting CTAs hold
             // the SMs -- CUDA gives no such forward-progress guarantee (it deadlocked on 8 GPUs), hence not the default.
@@ -763,7 +861,7 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
         } else {
             // interior box on the compute stream now; the boundary shell on its own stream as soon as the faces have
             // landed -- both launches share the GPU (no serialisation, no in-kernel waiting) and feed one ticket reduction
-            PPS_CUDA_CHECK(cudaEventRecord(h->ev_halo_done, h->halo_stream));
+            if (!use_p2p) PPS_CUDA_CHECK(cudaEventRecord(h->ev_halo_done, h->halo_stream));
             PPS_CUDA_CHECK(cudaEventRecord(h->ev_pre, h->stream));   // field updated, Neumann ghosts written
             Box inner;
             std::vector<Box> shell;
@@ -780,7 +878,14 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
             for (size_t q = 0; q < boxes.size(); q++) {
                 if (q == n_inner) {
                     PPS_CUDA_CHECK(cudaStreamWaitEvent(h->bnd_stream, h->ev_pre, 0));
-                    PPS_CUDA_CHECK(cudaStreamWaitEvent(h->bnd_stream, h->ev_halo_done, 0));
+                    if (use_p2p) {
+                        // the faces were pushed into my guard planes by the neighbours: wait for their epoch flags
+                        for (int up = 0; up < 2; up++)
+                            if (b.g.hc[4 + up])
+                                await_epoch_sys_kernel<<<1, 1, 0, h->bnd_stream>>>(h->recv_epoch + 2 * p2p_field + up, p2p_epoch);
+                    } else {
+                        PPS_CUDA_CHECK(cudaStreamWaitEvent(h->bnd_stream, h->ev_halo_done, 0));
+                    }
                     h->launch_stream = h->bnd_stream;
                 }
                 RedCtx red = make_red(h, nacc, total, off, op);
@@ -790,7 +895,7 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
             h->launch_stream = h->stream;
             PPS_CUDA_CHECK(cudaEventRecord(h->ev_bnd_done, h->bnd_stream));
             PPS_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_bnd_done, 0));
-            PPS_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_halo_done, 0));
+            if (!use_p2p) PPS_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_halo_done, 0));
         }
     }
     if (nacc > 0) finish_reduction(h, nacc, op, false);
@@ -955,6 +1060,12 @@ static void solve(pps_handle* h) {
     PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     if (h->halo_stream) PPS_CUDA_CHECK(cudaStreamSynchronize(h->halo_stream));   // exchanges of iterations launched past convergence
     if (h->bnd_stream) PPS_CUDA_CHECK(cudaStreamSynchronize(h->bnd_stream));
+    if (h->p2p) {
+        // peer-memory path: nobody may re-use or free its arrays while a neighbour still pushes into them -- my pushes are
+        // complete (halo stream synchronised above); this allreduce returns once every rank can say the same
+        PPS_NCCL_CHECK(nccl().AllReduce(h->ctl->sums + 6, h->ctl->sums + 6, 1, ncclDouble, ncclSum, h->comm, h->stream));
+        PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
     float ms = 0;
     PPS_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev_loop0, h->ev_loop1));
     h->loop_seconds = ms * 1e-3;
@@ -1108,6 +1219,7 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         PPS_CUDA_CHECK(cudaMalloc(&h->halo_flag, sizeof(unsigned int)));
         PPS_CUDA_CHECK(cudaMemsetAsync(h->halo_flag, 0, sizeof(unsigned int), h->stream));
     }
+    if (world > 1 && env_int("PPS_HALO_P2P", 0) && h->overlap) setup_p2p(h.get());
     h->ctl_host = Ctl{};
     h->ctl_host.norm_b = 1;
     upload_ctl(h.get());
@@ -1129,6 +1241,8 @@ static void destroy(pps_handle* h) {
     if (h->ev_field_ready) cudaEventDestroy(h->ev_field_ready);
     if (h->ev_halo_done) cudaEventDestroy(h->ev_halo_done);
     if (h->halo_flag) cudaFree(h->halo_flag);
+    for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
+    if (h->recv_epoch) cudaFree(h->recv_epoch);
     for (auto& b : h->blocks)
         for (double* p : b.owned) cudaFree(p);
     cudaFree(h->partials);

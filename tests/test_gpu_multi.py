@@ -26,11 +26,11 @@ def _free_port():
     return p
 
 
-def _run(layout, flags=()):
+def _run(layout, flags=(), env=None):
     n = layout[0] * layout[1] * layout[2]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "mg_check.py"), *map(str, layout), *flags]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, **(env or {})))
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-2000:])
     out = json.loads(lines[-1])
@@ -58,3 +58,17 @@ def test_eight_gpus(layout):
     if _ngpu() < 8:
         pytest.skip("needs 8 GPUs")
     _run(layout)
+
+
+EXPERIMENTAL = os.environ.get("PPS_TEST_EXPERIMENTAL") == "1"
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="experimental paths: set PPS_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("env", [{"PPS_HALO_P2P": "1"}, {"PPS_OVERLAP": "0"}, {"PPS_OVERLAP": "2"}])
+@pytest.mark.parametrize("flags", [(), ("cheb",)])
+def test_two_gpus_slab_transport_variants(env, flags):
+    """the same parity check with the peer-memory halo path (CUDA IPC + copy engines), the serial exchange and the
+    in-kernel-wait overlap"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run((1, 1, 2), flags, env)
