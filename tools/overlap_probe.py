@@ -8,6 +8,7 @@ Three timed variants of the same fixed-length BiCGSTAB loop on 1x1xN z-slabs (SU
   serial    PPS_OVERLAP=0         exchange, then the whole operator, on one stream
   overlap   PPS_OVERLAP=1         exchange on the halo stream while the interior box is computed
 hidden = 1 - (t_overlap - t_no_comm) / (t_serial - t_no_comm), times = device loop time per iteration, max over ranks.
+Optional extra variants: --p2p (PPS_HALO_P2P=1: CUDA-IPC peer pushes on copy engines), --inkernel (PPS_OVERLAP=2).
 """
 import json
 import os
@@ -27,7 +28,7 @@ import parallelpoissonsolver_b200 as pps  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    args = [int(a) for a in sys.argv[1:]]
+    args = [int(a) for a in sys.argv[1:] if not a.startswith("--")]
     npglobal = tuple(args[:3]) if len(args) >= 3 else (1024, 1024, 1024)
     iters = args[3] if len(args) >= 4 else 200
     torch.cuda.set_device(local)
@@ -35,8 +36,14 @@ def main():
     D = bench.Dist(rank, world, "cuda")
     X, B = bench.manufactured_slab(npglobal, world, rank)
     out = {"npglobal": npglobal, "world": world, "iters": iters}
-    for name, env in (("no_comm", {"PPS_DEBUG_NO_HALO": "1", "PPS_OVERLAP": "0"}), ("serial", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "0"}),
-                      ("overlap", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "1"})):
+    variants = [("no_comm", {"PPS_DEBUG_NO_HALO": "1", "PPS_OVERLAP": "0", "PPS_HALO_P2P": "0"}),
+                ("serial", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "0", "PPS_HALO_P2P": "0"}),
+                ("overlap", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "1", "PPS_HALO_P2P": "0"})]
+    if "--p2p" in sys.argv:
+        variants.append(("p2p", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "1", "PPS_HALO_P2P": "1"}))
+    if "--inkernel" in sys.argv:
+        variants.append(("inkernel", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "2", "PPS_HALO_P2P": "0"}))
+    for name, env in variants:
         os.environ.update(env)
         uid = D.bcast_bytes(pps.get_unique_id() if rank == 0 else None, 128)
         cfg = pps.make_config(npglobal, nranks=(1, 1, world), bcs=(0,) * 6, tolerance=1e-300, max_iter=iters, device=local)
@@ -57,6 +64,9 @@ def main():
     out["exposed_comm_ms_serial"] = tsr - tn
     out["exposed_comm_ms_overlap"] = to - tn
     out["hidden_fraction"] = 1 - (to - tn) / (tsr - tn) if tsr > tn else None
+    for extra in ("p2p", "inkernel"):
+        if extra + "_ms_per_iter" in out:
+            out["hidden_fraction_" + extra] = 1 - (out[extra + "_ms_per_iter"] - tn) / (tsr - tn) if tsr > tn else None
     if rank == 0:
         print(json.dumps(out), flush=True)
     dist.destroy_process_group()
