@@ -103,6 +103,7 @@ struct pps_handle {
     int lag = 3;
     bool operator_only = false; // PPS_FLAG_OPERATOR_ONLY: only p, v, r0 exist
     bool fuse_full = false;     // 17-pass schedule (single block, all-Dirichlet, no preconditioner)
+    bool fuse_p = true, fuse_s = true;   // PPS_FUSE_P / PPS_FUSE_S: enable the two fused kernels separately (diagnostics)
     int iter_in_solve = 0;      // host-side count of enqueued iterations of the running solve
     std::vector<Block> blocks;
     cudaStream_t stream = nullptr;
@@ -951,11 +952,7 @@ static void bicgstab_iteration_fused(pps_handle* h) {
     const Box box = b.g.solver_box();
     const Tiling ts = make_tiling(h, b.g, box, true);
     const Tiling tp = make_tiling(h, b.g, box, false);
-    if (h->iter_in_solve == 0) {
-        // first iteration: p0 = r0 is already in place (BiCGSTAB.hpp:125), plain operator
-        RedCtx red = make_red(h, 1, ts.ctas(), 0, OP_BICG_ALPHA);
-        launch_stencil(h, KC_APPLY_DOT, b, b.p, box, EpiStoreDot{b.v, b.r0}, red, ts, true);
-    } else {
+    if (h->iter_in_solve > 0 && h->fuse_p) {
         // p' = r + beta (p - omega v) ; v' = A p' ; sum r0.v' ; alpha            :262-272 of the previous pass + :142-164
         RedCtx red = make_red(h, 1, ts.ctas(), 0, OP_BICG_ALPHA);
         if (h->parity) launch_tma_pre<8, 4, true>(h, KC_FUSED_P, b, box, PrePUpdate<true>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, ts, true);
@@ -963,16 +960,37 @@ static void bicgstab_iteration_fused(pps_handle* h) {
         std::swap(b.p, b.p2);
         std::swap(b.v, b.v2);
         b.mp = b.p;
+    } else {
+        // first iteration (p0 = r0 is already in place, BiCGSTAB.hpp:125) or PPS_FUSE_P=0: p-update in place, plain operator
+        if (h->iter_in_solve > 0) {
+            RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
+            if (h->parity) launch_pointwise(h, KC_P_UPDATE, b, box, OpPUpdate<true>{b.p, b.r, b.v, 0, 0}, none, tp, true);
+            else           launch_pointwise(h, KC_P_UPDATE, b, box, OpPUpdate<false>{b.p, b.r, b.v, 0, 0}, none, tp, true);
+        }
+        RedCtx red = make_red(h, 1, ts.ctas(), 0, OP_BICG_ALPHA);
+        launch_stencil(h, KC_APPLY_DOT, b, b.p, box, EpiStoreDot{b.v, b.r0}, red, ts, true);
     }
-    {   // s = r - alpha v ; t = A s ; sum s.t, t.t ; omega                        :168-225
-        RedCtx red = make_red(h, 2, ts.ctas(), 0, OP_BICG_OMEGA);
-        if (h->parity) launch_tma_pre<8, 6, true>(h, KC_FUSED_S, b, box, PreSUpdate<true>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, ts, true);
-        else           launch_tma_pre<8, 6, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, ts, true);
-    }
-    {   // x += alpha p + omega s ; r = s - omega t ; sum r0.r, r.r ; beta, rho     :227-259
-        RedCtx red = make_red(h, 2, tp.ctas(), 0, OP_BICG_RHO);
-        if (h->parity) launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdateS<true>{b.x, b.r, b.p, b.s, b.t, b.r0, 0, 0}, red, tp, true);
-        else           launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdateS<false>{b.x, b.r, b.p, b.s, b.t, b.r0, 0, 0}, red, tp, true);
+    if (h->fuse_s) {
+        {   // s = r - alpha v ; t = A s ; sum s.t, t.t ; omega                        :168-225
+            RedCtx red = make_red(h, 2, ts.ctas(), 0, OP_BICG_OMEGA);
+            if (h->parity) launch_tma_pre<8, 6, true>(h, KC_FUSED_S, b, box, PreSUpdate<true>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, ts, true);
+            else           launch_tma_pre<8, 6, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, ts, true);
+        }
+        {   // x += alpha p + omega s ; r = s - omega t ; sum r0.r, r.r ; beta, rho     :227-259
+            RedCtx red = make_red(h, 2, tp.ctas(), 0, OP_BICG_RHO);
+            if (h->parity) launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdateS<true>{b.x, b.r, b.p, b.s, b.t, b.r0, 0, 0}, red, tp, true);
+            else           launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdateS<false>{b.x, b.r, b.p, b.s, b.t, b.r0, 0, 0}, red, tp, true);
+        }
+    } else {
+        // PPS_FUSE_S=0: the split kernels for this half (s lives in r)
+        RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
+        if (h->parity) launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<true>{b.r, b.v, 0}, none, tp, true);
+        else           launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<false>{b.r, b.v, 0}, none, tp, true);
+        RedCtx red2 = make_red(h, 2, ts.ctas(), 0, OP_BICG_OMEGA);
+        launch_stencil(h, KC_APPLY_DOT2, b, b.r, box, EpiStoreDot2Self{b.t}, red2, ts, true);
+        RedCtx red3 = make_red(h, 2, tp.ctas(), 0, OP_BICG_RHO);
+        if (h->parity) launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdate<true>{b.x, b.r, b.p, b.r, b.t, b.r0, 0, 0}, red3, tp, true);
+        else           launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdate<false>{b.x, b.r, b.p, b.r, b.t, b.r0, 0, 0}, red3, tp, true);
     }
     h->iter_in_solve++;
 }
@@ -1142,6 +1160,8 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         for (int f = 0; f < 6; f++) neumann = neumann || cfg.bcs_type[f] == 1;
         h->fuse_full = want == PPS_FUSE_FULL && world == 1 && nr == 1 && !neumann && !cheb && cfg.solver == PPS_SOLVER_BICGSTAB &&
                        h->stencil_impl == 1 && h->by_tma == 8;
+        h->fuse_p = env_int("PPS_FUSE_P", 1) != 0;
+        h->fuse_s = env_int("PPS_FUSE_S", 1) != 0;
     }
     unsigned long long max_ctas = 0;
     h->operator_only = (cfg.flags & PPS_FLAG_OPERATOR_ONLY) != 0;
