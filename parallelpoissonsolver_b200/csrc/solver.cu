@@ -385,7 +385,8 @@ template <class Op>
 static void launch_pointwise(pps_handle* h, int kc, const Block& b, const Box& box, const Op& op, const RedCtx& red,
                              const Tiling& t, bool check_done) {
     LaunchScope ls(h, kc);
-    // pointwise ops read their scalars from ctl in begin(); the done check is skipped by passing a flag-free view
+    // pointwise ops read their scalars from ctl in begin(), so they always get ctl and therefore always honour ctl->done;
+    // they are only launched inside the iteration or during set-up, where done == 0 (`check_done` documents the call site)
     const Ctl* ctl = h->ctl;
     (void)check_done;
     if (h->by == 4) pointwise_kernel<4, Op><<<t.grid, t.block, 0, h->stream>>>(b.g.dims, box, t.zchunk, t.org, op, red, ctl);
@@ -631,22 +632,16 @@ static void precondition(pps_handle* h, Block& b, double* X, double* B, bool che
     double rho_old = 1 / h->sigma;
     double rho = 1 / (2 * h->sigma - rho_old);
     neumann_ghosts(h, b, B, false, check_done);
-    const int last = m - 2;   // X = -y_last
-    if (last < 0) throw std::runtime_error("chebyshevMax < 2 is not supported");
+    const int last = m - 2;   // X = -y_last; validate() guarantees chebyshevMax >= 3, i.e. last >= 1
+    if (last < 1) throw std::runtime_error("chebyshevMax < 3 is not supported");
     const double c1 = 2 * rho / h->delta;
     double *Y = b.cy, *Z = b.cz, *W = b.cw;
     if (h->parity) {
         EpiChebFirst<true> e{Z, last == 1 ? X : Y, h->theta, 1.0 / h->theta, c1, last == 1 ? -1.0 : 1.0};
-        if (last == 0) { e.Z = X; e.Y = Y; }
         launch_stencil(h, KC_CHEB_FIRST, b, B, box, e, red, t, check_done);
     } else {
         EpiChebFirst<false> e{Z, last == 1 ? X : Y, h->theta, 1.0 / h->theta, c1, last == 1 ? -1.0 : 1.0};
-        if (last == 0) { e.Z = X; e.Y = Y; }
         launch_stencil(h, KC_CHEB_FIRST, b, B, box, e, red, t, check_done);
-    }
-    if (last == 0) {
-        // X = -y0 = -(B/theta): negate in place with a Chebyshev step of zero weight is overkill; handle by scaling
-        throw std::runtime_error("chebyshevMax == 2 is not supported");
     }
     for (int c = 2; c <= last; c++) {
         rho_old = rho;
@@ -1544,21 +1539,18 @@ int pps_bench_operator(pps_handle* h, int reps, int with_dot, double* avg_ms) {
     h->ctl_host.done = 0;
     upload_ctl(h);
     PPS_CUDA_CHECK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), h->stream));
-    const int saved_world = h->world;
     const bool with_halo = (with_dot & 2) != 0;
     with_dot &= 1;
     auto once = [&]() {
         if (with_halo) halo_exchange(h, sel_p, false);
         if (with_dot) {
             RedCtx red = make_red(h, 1, t.ctas(), 0, OP_NONE);
-            red.op = OP_NONE;
             launch_stencil(h, KC_APPLY_DOT, b, b.p, box, EpiStoreDot{b.v, b.r0}, red, t, false);
         } else {
             RedCtx red = make_red(h, 0, 1, 0, OP_NONE);
             launch_stencil(h, KC_APPLY, b, b.p, box, EpiStore{b.v}, red, t, false);
         }
     };
-    (void)saved_world;
     for (int i = 0; i < 3; i++) once();
     PPS_CUDA_CHECK(cudaEventRecord(e0, h->stream));
     for (int i = 0; i < reps; i++) once();
