@@ -615,6 +615,34 @@ __global__ void neumann_ghost_kernel(double* __restrict__ f, FaceGeom g, const d
     }
 }
 
+// all Neumann faces of a block in ONE launch (blockIdx.y = face slot): same arithmetic as neumann_ghost_kernel.  The faces
+// write disjoint ghost cells and read data cells only, so their order does not matter (iterativeSolverBase.hpp:69-168).
+struct GhostBatch {
+    FaceGeom g[6];
+    const double* dudn[6];
+    double two_ds[6];
+    int upper[6];
+    int count;
+};
+__global__ void neumann_ghost_batch_kernel(double* __restrict__ f, GhostBatch batch, const Ctl* ctl, int ignore_done) {
+    if (!ignore_done && ctl != nullptr && ctl->done) return;
+    const int q = blockIdx.y;
+    if (q >= batch.count) return;
+    const FaceGeom g = batch.g[q];
+    const double* dudn = batch.dudn[q];
+    const long long n = static_cast<long long>(g.nu) * g.nv;
+    for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < n;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long off = (t % g.nu) * g.stride_u + (t / g.nu) * g.stride_v;
+        double v = f[g.base_b + off];
+        if (dudn != nullptr) {
+            const double corr = __ddiv_rn(__dmul_rn(batch.two_ds[q], dudn[t]), ctl->norm_b);
+            v = batch.upper[q] ? __dadd_rn(v, corr) : __dsub_rn(v, corr);
+        }
+        f[g.base_a + off] = v;
+    }
+}
+
 // adjustFieldBForDirichletNeumanBCs (iterativeSolverBase.hpp:429-534), one face:
 //   Dirichlet: b(A = first interior plane) -= x(B = boundary plane) / ds^2        (:454, :502)
 //   Neumann:   b(A = boundary plane)      +/-= 2 dudn / ds                         (:480, :527)

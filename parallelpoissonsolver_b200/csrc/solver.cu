@@ -127,6 +127,7 @@ struct pps_handle {
     unsigned int halo_epoch = 0;
     HaloWait wait_next{nullptr, 0, -1, -1, 0};   // consumed by the next TMA operator launch
     int debug_no_halo = 0;            // timing experiments only: skip the exchange (wrong results)
+    int batch_ghosts = 0;             // PPS_BATCH_GHOSTS=1: all Neumann faces of a block in one launch (unverified, round 2)
     // peer-memory halo path (PPS_HALO_P2P=1, z-slabs): neighbours' field / flag arrays mapped through CUDA IPC
     bool p2p = false;
     double* peer_field[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [lo/hi neighbour][0 = Mp, 1 = z]
@@ -581,6 +582,25 @@ static void neumann_ghosts(pps_handle* h, Block& b, double* field, bool with_val
     for (int f = 0; f < 6; f++) any = any || (b.g.hb[f] && h->cfg.bcs_type[f] == 1);
     if (!any) return;
     LaunchScope ls(h, KC_GHOST);
+    if (h->batch_ghosts) {
+        GhostBatch batch{};
+        int blocks = 1;
+        for (int f = 0; f < 6; f++) {
+            if (!(b.g.hb[f] && h->cfg.bcs_type[f] == 1)) continue;
+            if (with_value && b.dudn[f] == nullptr)
+                throw std::runtime_error("Neumann face " + std::to_string(f) + " has no du/dn values: call pps_set_neumann_face first");
+            const int q = batch.count++;
+            batch.g[q] = face_geom(b.g, f, 0, 2);
+            batch.dudn[q] = with_value ? b.dudn[f] : nullptr;
+            batch.two_ds[q] = 2 * h->cfg.ds[f / 2];
+            batch.upper[q] = f % 2;
+            blocks = std::max(blocks, face_blocks(batch.g[q]));
+        }
+        neumann_ghost_batch_kernel<<<dim3(blocks, batch.count), 256, 0, h->stream>>>(field, batch, h->ctl, check_done ? 0 : 1);
+        ls.count(1);
+        check_launch("neumann_ghost_batch");
+        return;
+    }
     for (int f = 0; f < 6; f++) {
         if (!(b.g.hb[f] && h->cfg.bcs_type[f] == 1)) continue;
         FaceGeom g = face_geom(b.g, f, 0, 2);
@@ -1136,6 +1156,7 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     h->lag = env_int("PPS_LAG", 3);
     h->overlap = env_int("PPS_OVERLAP", 1);
     h->debug_no_halo = env_int("PPS_DEBUG_NO_HALO", 0);
+    h->batch_ghosts = env_int("PPS_BATCH_GHOSTS", 0);
     PPS_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->launch_stream = h->stream;
     for (int d = 0; d < 3; d++) {

@@ -338,3 +338,23 @@ def test_fused_schedule_is_bitwise_identical_to_split(np_, arith):
     assert np.array_equal(s_full.get_solution(0), s_split.get_solution(0))
     assert s_full.launch_count < s_split.launch_count          # 3 instead of 5 kernels per iteration
     s_full.close(); s_split.close(); o.close()
+
+
+EXPERIMENTAL = __import__("os").environ.get("PPS_TEST_EXPERIMENTAL") == "1"
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="unverified round-2 paths: set PPS_TEST_EXPERIMENTAL=1")
+def test_batched_neumann_ghosts_bitwise(monkeypatch):
+    """PPS_BATCH_GHOSTS=1 (all Neumann faces of a block in one launch) must not change a single bit"""
+    pps = _pps()
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PPS_BATCH_GHOSTS", mode)
+        o, s = _pair((24, 20, 28), nranks=(1, 1, 2), bcs=(1, 1, 0, 1, 1, 0), precond=po.PRECOND_CHEBYSHEV, arithmetic=pps.ARITH_PARITY)
+        o.set_problem()
+        H.hand_over_problem(o, s)
+        s.solve()
+        res[mode] = (s.history().copy(), s.get_solution(0).copy(), s.launch_count)
+        s.close(); o.close()
+    assert np.array_equal(res["0"][0], res["1"][0]) and np.array_equal(res["0"][1], res["1"][1])
+    assert res["1"][2] < res["0"][2]
