@@ -94,6 +94,16 @@ enum ScalarOp : int {
     OP_CG_BETA = 8,        // beta = sum(r.z)new / (r.z)old, err, iter++    baseCG.hpp:183-194,211-227
 };
 
+// Allreduce fused into the reducing kernel over peer memory (PPS_ALLREDUCE_P2P=1): the last CTA of the reduction writes
+// its sums into every rank's mailbox, waits for the mailboxes it receives and adds them up in rank order (identical bits
+// on every rank).  Mailbox of a rank: [2 parities][world][4] doubles, slot 3 = epoch (as a 64-bit integer), written last.
+struct PeerReduce {
+    double* const* peer_mail;   // device array of `world` pointers: every rank's mailbox (mine included)
+    double* my_mail;
+    unsigned int epoch;         // 0: disabled
+    int world, rank;
+};
+
 struct RedCtx {
     double* partials;          // [kMaxAcc][capacity]
     unsigned int* counter;     // ticket
@@ -103,6 +113,7 @@ struct RedCtx {
     int nacc;                  // accumulators in use
     int op;                    // ScalarOp applied by the last CTA (OP_NONE when an allreduce follows)
     Ctl* ctl;
+    PeerReduce pr;             // in-kernel allreduce across GPUs (pr.epoch != 0)
 };
 
 constexpr int kMaxAcc = 3;

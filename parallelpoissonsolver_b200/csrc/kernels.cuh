@@ -175,6 +175,45 @@ __device__ __forceinline__ void grid_reduce_finish(double (&acc)[NACC], const Re
     }
     __syncthreads();
     block_sum<NACC>(tot, sm, tid, nwarps);
+    if (red.pr.epoch != 0) {
+        // ---- allreduce over peer memory, fused into this kernel (see PeerReduce)
+        __shared__ double s_tot[NACC];
+        if (tid == 0) {
+#pragma unroll
+            for (int a = 0; a < NACC; a++) s_tot[a] = tot[a];
+        }
+        __syncthreads();
+        const int W = red.pr.world, R = red.pr.rank;
+        const unsigned long long e = red.pr.epoch;
+        const int par = static_cast<int>(e & 1ull);
+        if (tid < W) {
+            double* dst = red.pr.peer_mail[tid] + (static_cast<long long>(par) * W + R) * 4;
+#pragma unroll
+            for (int a = 0; a < NACC; a++) asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(dst + a), "d"(s_tot[a]) : "memory");
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst + 3), "l"(e) : "memory");
+            const double* src = red.pr.my_mail + (static_cast<long long>(par) * W + tid) * 4;
+            unsigned long long seen;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src + 3) : "memory");
+                if (seen == e) break;
+                __nanosleep(50);
+            } while (true);
+        }
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int a = 0; a < NACC; a++) {
+                double v = 0.0;
+                for (int r = 0; r < W; r++) {
+                    double x;
+                    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(x) : "l"(red.pr.my_mail + (static_cast<long long>(par) * W + r) * 4 + a) : "memory");
+                    v += x;
+                }
+                tot[a] = v;
+            }
+        }
+    }
     if (tid == 0) {
 #pragma unroll
         for (int a = 0; a < NACC; a++) red.ctl->sums[a] = tot[a];

@@ -135,6 +135,11 @@ struct pps_handle {
     unsigned int* recv_epoch = nullptr;                                    // mine: [field][face lo/hi], written by the neighbours
     unsigned int field_epoch[2] = {0, 0};
     std::vector<void*> ipc_opened;
+    // peer-memory allreduce fused into the reducing kernels (PPS_ALLREDUCE_P2P=1)
+    bool ar_p2p = false;
+    double* ar_mail = nullptr;            // my mailbox [2][world][4]
+    double** ar_peer_table = nullptr;     // device: world mailbox pointers
+    unsigned int ar_epoch = 0;
     Coef coef{};
     // Chebyshev constants (chebyshevIteration.hpp:22-26)
     double theta = 0, delta = 0, sigma = 0;
@@ -279,6 +284,13 @@ static RedCtx make_red(pps_handle* h, int nacc, unsigned int total, unsigned int
     r.nacc = nacc;
     r.op = (h->world > 1) ? static_cast<int>(OP_NONE) : op;
     r.ctl = h->ctl;
+    r.pr = PeerReduce{nullptr, nullptr, 0, 0, 0};
+    if (h->ar_p2p && nacc > 0 && op != OP_NONE) {
+        // the allreduce happens inside the reducing kernel: every launch that feeds this reduction carries the same epoch
+        // (finish_reduction bumps it once the launches of the reduction have been issued)
+        r.op = op;
+        r.pr = PeerReduce{h->ar_peer_table, h->ar_mail, h->ar_epoch + 1, h->world, h->rank};
+    }
     if (total > h->partial_capacity) throw std::runtime_error("partials buffer too small");
     return r;
 }
@@ -286,6 +298,10 @@ static RedCtx make_red(pps_handle* h, int nacc, unsigned int total, unsigned int
 // after a fused reduction: allreduce the raw sums over NVLink and apply the scalar update (world > 1 only)
 static void finish_reduction(pps_handle* h, int nacc, int op, bool ignore_done) {
     if (h->world == 1) return;
+    if (h->ar_p2p && op != OP_NONE) {
+        h->ar_epoch++;   // done in-kernel (PeerReduce); next reduction, next epoch
+        return;
+    }
     LaunchScope ls(h, KC_SCALAR);
     PPS_NCCL_CHECK(nccl().AllReduce(h->ctl->sums, h->ctl->sums, nacc, ncclDouble, ncclSum, h->comm, h->stream));
     scalar_op_kernel<<<1, 1, 0, h->stream>>>(op, h->ctl, ignore_done ? 1 : 0);
@@ -555,6 +571,49 @@ static void setup_p2p(pps_handle* h) {
         }
     }
     h->p2p = true;
+}
+
+// mailboxes of the in-kernel allreduce: exchange IPC handles with EVERY rank
+static void setup_allreduce_p2p(pps_handle* h) {
+    struct Info { long long pid; int device; int pad; cudaIpcMemHandle_t mail; unsigned long long raw; };
+    const size_t bytes = sizeof(double) * 2 * 4 * static_cast<size_t>(h->world);
+    PPS_CUDA_CHECK(cudaMalloc(&h->ar_mail, bytes));
+    PPS_CUDA_CHECK(cudaMemsetAsync(h->ar_mail, 0, bytes, h->stream));
+    Info mine{};
+    mine.pid = static_cast<long long>(getpid());
+    mine.device = h->device;
+    PPS_CUDA_CHECK(cudaIpcGetMemHandle(&mine.mail, h->ar_mail));
+    mine.raw = reinterpret_cast<unsigned long long>(h->ar_mail);
+    const size_t sz = sizeof(Info);
+    char* scratch = reinterpret_cast<char*>(h->partials);
+    PPS_CUDA_CHECK(cudaMemcpyAsync(scratch + sz * h->rank, &mine, sz, cudaMemcpyHostToDevice, h->stream));
+    PPS_NCCL_CHECK(nccl().AllGather(scratch + sz * h->rank, scratch, sz, ncclChar, h->comm, h->stream));
+    std::vector<Info> all(h->world);
+    PPS_CUDA_CHECK(cudaMemcpyAsync(all.data(), scratch, sz * h->world, cudaMemcpyDeviceToHost, h->stream));
+    PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    std::vector<double*> table(h->world, nullptr);
+    for (int r = 0; r < h->world; r++) {
+        if (r == h->rank) { table[r] = h->ar_mail; continue; }
+        if (all[r].pid == mine.pid) {
+            if (all[r].device != h->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PPS_CUDA_CHECK(e);
+                cudaGetLastError();
+            }
+            table[r] = reinterpret_cast<double*>(all[r].raw);
+        } else {
+            void* q = nullptr;
+            PPS_CUDA_CHECK(cudaIpcOpenMemHandle(&q, all[r].mail, cudaIpcMemLazyEnablePeerAccess));
+            table[r] = static_cast<double*>(q);
+            h->ipc_opened.push_back(q);
+        }
+    }
+    PPS_CUDA_CHECK(cudaMalloc(&h->ar_peer_table, sizeof(double*) * h->world));
+    PPS_CUDA_CHECK(cudaMemcpyAsync(h->ar_peer_table, table.data(), sizeof(double*) * h->world, cudaMemcpyHostToDevice, h->stream));
+    // nobody may post into a mailbox before it has been cleared: one more collective as a barrier
+    PPS_NCCL_CHECK(nccl().AllReduce(h->ctl->sums + 7, h->ctl->sums + 7, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->ar_p2p = true;
 }
 
 // push my boundary planes of field `fidx` (0 = Mp, 1 = z) into the neighbours' guard planes on the halo stream
@@ -1256,6 +1315,7 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         PPS_CUDA_CHECK(cudaMemsetAsync(h->halo_flag, 0, sizeof(unsigned int), h->stream));
     }
     if (world > 1 && env_int("PPS_HALO_P2P", 0) && h->overlap) setup_p2p(h.get());
+    if (world > 1 && world <= 256 && env_int("PPS_ALLREDUCE_P2P", 0)) setup_allreduce_p2p(h.get());
     h->ctl_host = Ctl{};
     h->ctl_host.norm_b = 1;
     upload_ctl(h.get());
@@ -1279,6 +1339,8 @@ static void destroy(pps_handle* h) {
     if (h->halo_flag) cudaFree(h->halo_flag);
     for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
     if (h->recv_epoch) cudaFree(h->recv_epoch);
+    if (h->ar_mail) cudaFree(h->ar_mail);
+    if (h->ar_peer_table) cudaFree(h->ar_peer_table);
     for (auto& b : h->blocks)
         for (double* p : b.owned) cudaFree(p);
     cudaFree(h->partials);

@@ -64,7 +64,8 @@ EXPERIMENTAL = os.environ.get("PPS_TEST_EXPERIMENTAL") == "1"
 
 
 @pytest.mark.skipif(not EXPERIMENTAL, reason="experimental paths: set PPS_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("env", [{"PPS_HALO_P2P": "1"}, {"PPS_OVERLAP": "0"}, {"PPS_OVERLAP": "2"}])
+@pytest.mark.parametrize("env", [{"PPS_HALO_P2P": "1"}, {"PPS_ALLREDUCE_P2P": "1"}, {"PPS_HALO_P2P": "1", "PPS_ALLREDUCE_P2P": "1"},
+                                 {"PPS_OVERLAP": "0"}, {"PPS_OVERLAP": "2"}])
 @pytest.mark.parametrize("flags", [(), ("cheb",)])
 def test_two_gpus_slab_transport_variants(env, flags):
     """the same parity check with the peer-memory halo path (CUDA IPC + copy engines), the serial exchange and the
