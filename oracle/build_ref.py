@@ -38,6 +38,10 @@ SOLVER_TYPEDEFS = {
     "bicgstab_cheb": "BiCGSTAB<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, T_Preconditioner2>",
     "cg_none": "BaseCG<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, T_NoneSolver>",
     "cg_cheb": "BaseCG<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, T_Preconditioner2>",
+    # nested Krylov preconditioners: the local BiCGSTAB of inputParam.hpp:31 and the local CG with
+    # Chebyshev inside of inputParam.hpp:29 in the preconditioner slot
+    "bicgstab_bicgloc": "BiCGSTAB<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, T_Preconditioner>",
+    "bicgstab_cgcheb": "BiCGSTAB<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, T_Preconditioner3>",
 }
 
 DIRICHLET = (0, 0, 0, 0, 0, 0)
@@ -67,6 +71,8 @@ CONFIGS = {
     "cg32": cfg((32, 32, 32), solver="cg_none"),
     "cg32_cheb": cfg((32, 32, 32), solver="cg_cheb"),
     "cgm24": cfg((24, 20, 28), MIXED, "cg_none", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1)),
+    "nb24": cfg((24, 20, 28), MIXED, "bicgstab_bicgloc", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1)),
+    "nc24": cfg((24, 20, 28), MIXED, "bicgstab_cgcheb", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1)),
     "d128": cfg((128, 128, 128)),
     # CPU-baseline samples for bench.py --impl reference (bounded: fixed iteration count)
     "bench256": cfg((256, 256, 256), iter_max=10000),

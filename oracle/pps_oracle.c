@@ -23,6 +23,7 @@ typedef struct {
     double *x, *b;
     double *p, *r, *r0, *Mp, *AMp, *z, *Az; /* BiCGSTAB.hpp:23-29 ; CG uses p, r, AMp(=Apk), z */
     double *cy, *cz, *cw;                   /* chebyshevIteration.hpp:28-30 */
+    double *lw[7];                          /* work arrays of a nested (local) Krylov preconditioner: p r r0 Mp AMp z Az */
 } Block;
 
 struct orc {
@@ -58,6 +59,8 @@ void orc_default_config(orc_config* c) {
     c->cheb_epsilon = 1e-4;
     c->cheb_rescale_min = 500;
     c->cheb_rescale_max = 1 - 1e-4;
+    c->precond_tolerance = 1e4 * 1e-10;
+    c->precond_max_iter = 150;
 }
 
 /* ---------------------------------------------------------------- geometry (blockGrid.hpp) */
@@ -118,7 +121,9 @@ orc_t* orc_create(const orc_config* c) {
         B->x = zalloc(B->ntot); B->b = zalloc(B->ntot);
         B->p = zalloc(B->ntot); B->r = zalloc(B->ntot); B->r0 = zalloc(B->ntot);
         B->Mp = zalloc(B->ntot); B->AMp = zalloc(B->ntot); B->z = zalloc(B->ntot); B->Az = zalloc(B->ntot);
-        if (c->precond == ORC_PRECOND_CHEBYSHEV) { B->cy = zalloc(B->ntot); B->cz = zalloc(B->ntot); B->cw = zalloc(B->ntot); }
+        if (c->precond == ORC_PRECOND_CHEBYSHEV || c->precond == ORC_PRECOND_CG_CHEB_LOCAL) { B->cy = zalloc(B->ntot); B->cz = zalloc(B->ntot); B->cw = zalloc(B->ntot); }
+        if (c->precond == ORC_PRECOND_BICGSTAB_LOCAL || c->precond == ORC_PRECOND_CG_CHEB_LOCAL)
+            for (int q = 0; q < 7; q++) B->lw[q] = zalloc(B->ntot);
     }
     const double* eg = o->blk[0].eig_global;
     /* chebyshevIteration.hpp:22-26 (global eigenvalues; delta is negative) */
@@ -139,6 +144,7 @@ void orc_destroy(orc_t* o) {
         Block* B = &o->blk[r];
         free(B->x); free(B->b); free(B->p); free(B->r); free(B->r0); free(B->Mp); free(B->AMp); free(B->z); free(B->Az);
         free(B->cy); free(B->cz); free(B->cw);
+        for (int q = 0; q < 7; q++) free(B->lw[q]);
     }
     free(o->blk); free(o->hist); free(o->h_alpha); free(o->h_omega); free(o->h_rho);
     free(o);
@@ -403,9 +409,121 @@ static void chebyshev_block(orc_t* o, int rank, double* X, double* Bf) {
     FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; X[q] = (-1) * B->cw[q]; }
 }
 
+/* ---- nested Krylov preconditioners: isMainLoop = false, communicationON = false -> everything is rank-local.
+ * X is zeroed, B is normalised by its own norm over the solver range and multiplied back at the end (so the CALLER's
+ * vector changes in the last bits, as in the reference), Neumann ghosts are plain mirrors. */
+static double local_norm_and_scale(const Block* B, double* X, double* Bf) {
+    /* normalizeProblemToFieldBNorm<false, false>: iterativeSolverBase.hpp:171-234 */
+    double s = 0.0;
+    FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; s += Bf[q] * Bf[q]; }
+    const double nrm = sqrt(s);
+    for (long q = 0; q < B->ntot; q++) { X[q] /= nrm; Bf[q] /= nrm; }
+    return nrm;
+}
+static double local_residual(const orc_t* o, int rank, double* X, const double* Bf, double* r) {
+    /* computeErrorOperatorA<false, false>: iterativeSolverBase.hpp:236-280 */
+    const Block* B = &o->blk[rank];
+    orc_reset_neumann(o, rank, X, 0, 1.0);
+    double s = 0.0;
+    FOR_SOLVER(B, i, j, k) {
+        const long q = i + B->sj * j + B->sk * k;
+        r[q] = Bf[q] - stencil(o, B, X, i, j, k);
+        s += r[q] * r[q];
+    }
+    return sqrt(s);
+}
+
+static void local_bicgstab(orc_t* o, int rank, double* X, double* Bf) {
+    /* BiCGSTAB.hpp:55-322 with isMainLoop = false, communicationON = false, T_Preconditioner = NoneSolver */
+    Block* B = &o->blk[rank];
+    double *p = B->lw[0], *r = B->lw[1], *r0 = B->lw[2], *Mp = B->lw[3], *AMp = B->lw[4], *z = B->lw[5], *Az = B->lw[6];
+    const size_t nb = sizeof(double) * (size_t)B->ntot;
+    for (int q = 0; q < 7; q++) memset(B->lw[q], 0, nb);
+    memset(X, 0, nb);                                                              /* :96 */
+    const double nrm = local_norm_and_scale(B, X, Bf);
+    const double err0 = local_residual(o, rank, X, Bf, r);
+    if (err0 < o->c.precond_tolerance) return;                                     /* :118-122: returns without de-normalising */
+    memcpy(p, r, nb);
+    memcpy(r0, r, nb);
+    double alphak = 1, omegak = 1, betak = 1, rho0 = 1, rho1 = 1, err = 0;
+    int iter = 0;
+    (void)betak;
+    while (iter < o->c.precond_max_iter) {
+        memcpy(Mp, p, nb);
+        orc_reset_neumann(o, rank, Mp, 0, 1.0);
+        double s1 = 0.0, s2 = 0.0;
+        FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; AMp[q] = stencil(o, B, Mp, i, j, k); s2 += r0[q] * AMp[q]; }
+        alphak = rho0 / s2;
+        FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; r[q] = r[q] - alphak * AMp[q]; }
+        memcpy(z, r, nb);
+        orc_reset_neumann(o, rank, z, 0, 1.0);
+        FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; Az[q] = stencil(o, B, z, i, j, k); }
+        s1 = 0.0; s2 = 0.0;
+        FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; s1 += r[q] * Az[q]; s2 += Az[q] * Az[q]; }
+        omegak = s1 / s2;
+        for (long q = 0; q < B->ntot; q++) X[q] = X[q] + alphak * Mp[q] + omegak * z[q];
+        s1 = 0.0; s2 = 0.0;
+        FOR_SOLVER(B, i, j, k) {
+            const long q = i + B->sj * j + B->sk * k;
+            r[q] = r[q] - omegak * Az[q];
+            s1 += r0[q] * r[q];
+            s2 += r[q] * r[q];
+        }
+        err = sqrt(s2);
+        rho1 = s1;
+        betak = rho1 / rho0 * alphak / omegak;
+        rho0 = rho1;
+        FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; p[q] = r[q] + betak * (p[q] - omegak * AMp[q]); }
+        iter++;
+        if (err < o->c.precond_tolerance) break;
+    }
+    orc_reset_neumann(o, rank, X, 0, 1.0);                                         /* :300 */
+    for (long q = 0; q < B->ntot; q++) { X[q] *= nrm; Bf[q] *= nrm; }              /* :310-314 */
+}
+
+static void chebyshev_block(orc_t* o, int rank, double* X, double* Bf);
+
+static void local_cg_chebyshev(orc_t* o, int rank, double* X, double* Bf) {
+    /* baseCG.hpp:44-260 with isMainLoop = false, communicationON = false, T_Preconditioner = ChebyshevIteration */
+    Block* B = &o->blk[rank];
+    double *p = B->lw[0], *r = B->lw[1], *Ap = B->lw[2], *z = B->lw[3];
+    const size_t nb = sizeof(double) * (size_t)B->ntot;
+    for (int q = 0; q < 4; q++) memset(B->lw[q], 0, nb);
+    memset(X, 0, nb);
+    const double nrm = local_norm_and_scale(B, X, Bf);
+    const double err0 = local_residual(o, rank, X, Bf, r);
+    if (err0 < o->c.precond_tolerance) return;
+    chebyshev_block(o, rank, z, r);
+    memcpy(p, z, nb);
+    double alphak = 1, betak = 1, s1 = 0, s2 = 0, srk = 1, err = 0;
+    int iter = 0;
+    while (iter < o->c.precond_max_iter) {
+        s1 = 0.0; s2 = 0.0;
+        FOR_SOLVER(B, i, j, k) {
+            const long q = i + B->sj * j + B->sk * k;
+            Ap[q] = stencil(o, B, p, i, j, k);
+            s1 += r[q] * z[q];
+            s2 += p[q] * Ap[q];
+        }
+        alphak = s1 / s2;
+        FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; X[q] = X[q] + alphak * p[q]; r[q] = r[q] - alphak * Ap[q]; }
+        chebyshev_block(o, rank, z, r);
+        s2 = 0.0; srk = 0.0;
+        FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; s2 += r[q] * z[q]; srk += r[q] * r[q]; }
+        betak = s2 / s1;
+        err = sqrt(srk);
+        FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; p[q] = z[q] + betak * p[q]; }
+        iter++;
+        if (err < o->c.precond_tolerance) break;
+    }
+    for (long q = 0; q < B->ntot; q++) { X[q] *= nrm; Bf[q] *= nrm; }
+}
+
 void orc_precondition(orc_t* o, double* const* X, double* const* Bf) {
     for (int r = 0; r < o->world; r++) {
         if (o->c.precond == ORC_PRECOND_CHEBYSHEV) chebyshev_block(o, r, X[r], Bf[r]);
+        else if (o->c.precond == ORC_PRECOND_BICGSTAB_LOCAL) local_bicgstab(o, r, X[r], Bf[r]);
+        else if (o->c.precond == ORC_PRECOND_CG_CHEB_LOCAL) local_cg_chebyshev(o, r, X[r], Bf[r]);
         else memcpy(X[r], Bf[r], sizeof(double) * (size_t)o->blk[r].ntot);   /* noneSolver.hpp:24-27 */
     }
 }

@@ -21,7 +21,10 @@ extern "C" {
 #endif
 
 enum { ORC_SOLVER_BICGSTAB = 0, ORC_SOLVER_CG = 1 };
-enum { ORC_PRECOND_NONE = 0, ORC_PRECOND_CHEBYSHEV = 1 };
+enum { ORC_PRECOND_NONE = 0,            /* T_NoneSolver,       inputParam.hpp:24 */
+       ORC_PRECOND_CHEBYSHEV = 1,       /* T_Preconditioner2,  inputParam.hpp:28 */
+       ORC_PRECOND_BICGSTAB_LOCAL = 2,  /* T_Preconditioner,   inputParam.hpp:31: BiCGSTAB, isMainLoop false, communicationOFF, NoneSolver inside */
+       ORC_PRECOND_CG_CHEB_LOCAL = 3    /* T_Preconditioner3,  inputParam.hpp:29: BaseCG, isMainLoop false, communicationOFF, Chebyshev inside */ };
 
 typedef struct orc_config {
     int np[3];            /* npglobal            inputParam.hpp:41 */
@@ -37,6 +40,8 @@ typedef struct orc_config {
     double cheb_epsilon;  /* epsilon             solverSetup.hpp:37 */
     double cheb_rescale_min; /* rescaleEigMin    solverSetup.hpp:38 */
     double cheb_rescale_max; /* rescaleEigMax    solverSetup.hpp:39 */
+    double precond_tolerance; /* tollPreconditionerSolver * tollScalingFactor   solverSetup.hpp:31 (nested Krylov preconditioners) */
+    int precond_max_iter;     /* iterMaxPreconditioner   solverSetup.hpp:32 */
 } orc_config;
 
 typedef struct orc_block_info {

@@ -44,6 +44,9 @@ CASES = [
     ("d32", (1, 1, 4), False), ("d32", (4, 1, 1), False), ("d32_cheb", (1, 4, 1), False), ("d32_cheb", (1, 1, 4), True),
     ("m24", (3, 1, 1), False), ("m24", (1, 1, 4), False), ("m24_cheb", (3, 2, 1), False), ("m24_cheb", (1, 1, 4), False),
     ("cg32", (1, 1, 4), False), ("cg32_cheb", (4, 2, 1), False), ("d64", (1, 1, 8), False), ("d64_cheb", (1, 1, 8), False),
+    # nested Krylov preconditioners
+    ("nb24", (1, 1, 1), True), ("nb24", (1, 1, 2), False), ("nb24", (3, 1, 2), False),
+    ("nc24", (1, 1, 1), True), ("nc24", (2, 2, 1), False), ("nc24", (3, 1, 2), False),
 ]
 
 

@@ -23,7 +23,7 @@ def load_golden(name):
 
 def oracle_config_from_golden(g, nranks=None, max_iter=None, tolerance=None):
     solver = po.SOLVER_CG if str(g["solver"]) == "cg" else po.SOLVER_BICGSTAB
-    precond = po.PRECOND_CHEBYSHEV if str(g["precond"]) == "cheb" else po.PRECOND_NONE
+    precond = {"cheb": po.PRECOND_CHEBYSHEV, "bicgloc": po.PRECOND_BICGSTAB_LOCAL, "cgcheb": po.PRECOND_CG_CHEB_LOCAL}.get(str(g["precond"]), po.PRECOND_NONE)
     return po.make_config(
         np_=[int(v) for v in g["np"]], nranks=[int(v) for v in (g["nranks"] if nranks is None else nranks)],
         ds=[float(v) for v in g["ds"]], origin=[float(v) for v in g["origin"]], bcs=[int(v) for v in g["bcs"]],
