@@ -42,6 +42,8 @@ SOLVER_TYPEDEFS = {
     # Chebyshev inside of inputParam.hpp:29 in the preconditioner slot
     "bicgstab_bicgloc": "BiCGSTAB<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, T_Preconditioner>",
     "bicgstab_cgcheb": "BiCGSTAB<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, T_Preconditioner3>",
+    # Chebyshev iteration as the MAIN solver (chebyshevIteration.hpp:61-67,132-139): isMainLoop = true, communicationON
+    "cheb_main": "ChebyshevIteration<DIM, T_data, tollMainSolver, chebyshevMax, true, communicationON, T_NoneSolver>",
 }
 
 DIRICHLET = (0, 0, 0, 0, 0, 0)
@@ -49,9 +51,10 @@ MIXED = (0, 1, 0, 1, 0, 1)  # shipped default
 
 
 def cfg(np, bcs=DIRICHLET, solver="bicgstab_none", ds=(0.1, 0.1, 0.1), origin=(0, 0, 0), toll_scaling=1e-10,
-        toll_main=100, iter_max=1700, cheb_max=11):
+        toll_main=100, iter_max=1700, cheb_max=11, order_neumann=2, rescale_min=None, rescale_max=None):
     return dict(np=tuple(np), bcs=tuple(bcs), solver=solver, ds=tuple(ds), origin=tuple(origin),
-                toll_scaling=toll_scaling, toll_main=toll_main, iter_max=iter_max, cheb_max=cheb_max)
+                toll_scaling=toll_scaling, toll_main=toll_main, iter_max=iter_max, cheb_max=cheb_max,
+                order_neumann=order_neumann, rescale_min=rescale_min, rescale_max=rescale_max)
 
 
 # name -> configuration.  "default" is the reference exactly as shipped.
@@ -73,6 +76,13 @@ CONFIGS = {
     "cgm24": cfg((24, 20, 28), MIXED, "cg_none", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1)),
     "nb24": cfg((24, 20, 28), MIXED, "bicgstab_bicgloc", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1)),
     "nc24": cfg((24, 20, 28), MIXED, "bicgstab_cgcheb", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1)),
+    # first-order Neumann closure (solverSetup.hpp:25 orderNeumanBcs = 1) and Chebyshev as main solver
+    "o1m24": cfg((24, 20, 28), MIXED, "bicgstab_none", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), order_neumann=1),
+    "o1m24_cheb": cfg((24, 20, 28), MIXED, "bicgstab_cheb", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), order_neumann=1),
+    "o1cgm24": cfg((24, 20, 28), MIXED, "cg_none", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), order_neumann=1),
+    "chm24": cfg((24, 20, 28), MIXED, "cheb_main", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), cheb_max=60,
+                 rescale_min=1.0, rescale_max=1.0),
+    "chd32": cfg((32, 32, 32), DIRICHLET, "cheb_main", cheb_max=25),
     "d128": cfg((128, 128, 128)),
     # CPU-baseline samples for bench.py --impl reference (bounded: fixed iteration count)
     "bench256": cfg((256, 256, 256), iter_max=10000),
@@ -115,6 +125,11 @@ def make_cfg_dir(name, c):
     t = _sub(t, r"tollMainSolver=[^;]*;", "tollMainSolver=%d;" % c["toll_main"], p)
     t = _sub(t, r"iterMaxMainSolver=[^;]*;", "iterMaxMainSolver=%d;" % c["iter_max"], p)
     t = _sub(t, r"chebyshevMax=[^;]*;", "chebyshevMax=%d;" % c["cheb_max"], p)
+    t = _sub(t, r"orderNeumanBcs=[^;]*;", "orderNeumanBcs=%d;" % c.get("order_neumann", 2), p)
+    if c.get("rescale_min") is not None:
+        t = _sub(t, r"rescaleEigMin= [^;]*;", "rescaleEigMin= %s;" % _fmt(float(c["rescale_min"])), p)
+    if c.get("rescale_max") is not None:
+        t = _sub(t, r"rescaleEigMax= [^;]*;", "rescaleEigMax= %s;" % _fmt(float(c["rescale_max"])), p)
     open(p, "w").write(t)
     return dst
 
@@ -168,7 +183,8 @@ def build_one(name, shim_obj, force=False):
     obj = os.path.join(cfgdir, "ref_main.o")
     _run([CXX] + CXXFLAGS + inc + ["-Dmain=ref_main", "-c", os.path.join(REF_CPU, "src", "main.cpp"), "-o", obj])
     _run([CXX] + CXXFLAGS + inc + [obj, os.path.join(HERE, "ref_launcher.cpp"), shim_obj, "-o", solver_bin])
-    _run([CXX] + CXXFLAGS + inc + [os.path.join(HERE, "ref_dump.cpp"), shim_obj, "-o", dump_bin])
+    dump_defs = ["-DPPS_DUMP_SKIP_NORM"] if c["solver"] == "cheb_main" else []
+    _run([CXX] + CXXFLAGS + dump_defs + inc + [os.path.join(HERE, "ref_dump.cpp"), shim_obj, "-o", dump_bin])
     return solver_bin, dump_bin
 
 

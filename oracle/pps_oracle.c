@@ -61,6 +61,7 @@ void orc_default_config(orc_config* c) {
     c->cheb_rescale_max = 1 - 1e-4;
     c->precond_tolerance = 1e4 * 1e-10;
     c->precond_max_iter = 150;
+    c->order_neumann = 2;
 }
 
 /* ---------------------------------------------------------------- geometry (blockGrid.hpp) */
@@ -113,6 +114,7 @@ static double* zalloc(long n) { return (double*)calloc((size_t)n, sizeof(double)
 orc_t* orc_create(const orc_config* c) {
     orc_t* o = (orc_t*)calloc(1, sizeof(orc_t));
     o->c = *c;
+    if (o->c.order_neumann != 1) o->c.order_neumann = 2;
     o->world = c->nranks[0] * c->nranks[1] * c->nranks[2];
     o->blk = (Block*)calloc((size_t)o->world, sizeof(Block));
     for (int r = 0; r < o->world; r++) {
@@ -121,7 +123,7 @@ orc_t* orc_create(const orc_config* c) {
         B->x = zalloc(B->ntot); B->b = zalloc(B->ntot);
         B->p = zalloc(B->ntot); B->r = zalloc(B->ntot); B->r0 = zalloc(B->ntot);
         B->Mp = zalloc(B->ntot); B->AMp = zalloc(B->ntot); B->z = zalloc(B->ntot); B->Az = zalloc(B->ntot);
-        if (c->precond == ORC_PRECOND_CHEBYSHEV || c->precond == ORC_PRECOND_CG_CHEB_LOCAL) { B->cy = zalloc(B->ntot); B->cz = zalloc(B->ntot); B->cw = zalloc(B->ntot); }
+        if (c->precond == ORC_PRECOND_CHEBYSHEV || c->precond == ORC_PRECOND_CG_CHEB_LOCAL || c->solver == ORC_SOLVER_CHEBYSHEV) { B->cy = zalloc(B->ntot); B->cz = zalloc(B->ntot); B->cw = zalloc(B->ntot); }
         if (c->precond == ORC_PRECOND_BICGSTAB_LOCAL || c->precond == ORC_PRECOND_CG_CHEB_LOCAL)
             for (int q = 0; q < 7; q++) B->lw[q] = zalloc(B->ntot);
     }
@@ -130,7 +132,7 @@ orc_t* orc_create(const orc_config* c) {
     o->theta = (eg[0] * c->cheb_rescale_min + eg[1] * c->cheb_rescale_max) * 0.5 * (1.0 + c->cheb_epsilon);
     o->delta = (eg[0] * c->cheb_rescale_min - eg[1] * c->cheb_rescale_max) * 0.5;
     o->sigma = o->theta / o->delta;
-    const long nh = (long)c->max_iter + 2;
+    const long nh = (long)(c->max_iter > c->cheb_max ? c->max_iter : c->cheb_max) + 2;
     o->hist = zalloc(nh); o->h_alpha = zalloc(nh); o->h_omega = zalloc(nh); o->h_rho = zalloc(nh);
     o->norm_b = 1.0;
     o->err_iter = -1.0;
@@ -272,7 +274,8 @@ void orc_halo_exchange(const orc_t* o, double* const* f) {
     }
 }
 
-/* resetNeumanBCs<isMainLoop, fieldData>, orderNeumanBcs == 2: iterativeSolverBase.hpp:62-169 */
+/* resetNeumanBCs<isMainLoop, fieldData>: iterativeSolverBase.hpp:62-169.  orderNeumanBcs == 2 mirrors the first interior
+ * plane (step 2 ds), orderNeumanBcs == 1 copies the boundary plane itself (step ds). */
 void orc_reset_neumann(const orc_t* o, int rank, double* field, int with_bc_value, double norm_b) {
     const Block* B = &o->blk[rank];
     for (int dir = 0; dir < 3; dir++) {
@@ -288,19 +291,25 @@ void orc_reset_neumann(const orc_t* o, int rank, double* field, int with_bc_valu
                     for (int i = lim[0]; i < lim[1]; i++) {
                         const long g = (i - adj[0]) + B->sj * (j - adj[1]) + B->sk * (k - adj[2]);
                         const long m = (i + adj[0]) + B->sj * (j + adj[1]) + B->sk * (k + adj[2]);
+                        const long bd = i + B->sj * j + B->sk * k;
                         if (with_bc_value) {
                             const double dn = orc_exact_dudn(coord(o, B, 0, i), coord(o, B, 1, j), coord(o, B, 2, k), dir);
-                            if (!up) field[g] = field[m] - 2 * o->c.ds[dir] * dn / norm_b;   /* :105 */
-                            else     field[g] = field[m] + 2 * o->c.ds[dir] * dn / norm_b;   /* :153 */
+                            if (o->c.order_neumann == 1) {
+                                if (!up) field[g] = field[bd] - o->c.ds[dir] * dn / norm_b;  /* :95 */
+                                else     field[g] = field[bd] + o->c.ds[dir] * dn / norm_b;  /* :143 */
+                            } else {
+                                if (!up) field[g] = field[m] - 2 * o->c.ds[dir] * dn / norm_b;   /* :100 */
+                                else     field[g] = field[m] + 2 * o->c.ds[dir] * dn / norm_b;   /* :148 */
+                            }
                         } else {
-                            field[g] = field[m];                                             /* :118, :166 */
+                            field[g] = o->c.order_neumann == 1 ? field[bd] : field[m];       /* :108 / :113, :156 / :161 */
                         }
                     }
         }
     }
 }
 
-/* adjustFieldBForDirichletNeumanBCs, orderNeumanBcs == 2: iterativeSolverBase.hpp:429-534 */
+/* adjustFieldBForDirichletNeumanBCs: iterativeSolverBase.hpp:429-534 */
 void orc_adjust_b(const orc_t* o, int rank, const double* x, double* b) {
     const Block* B = &o->blk[rank];
     for (int dir = 0; dir < 3; dir++) {
@@ -321,8 +330,13 @@ void orc_adjust_b(const orc_t* o, int rank, const double* x, double* b) {
                             b[ib] -= x[ix] / (ds * ds);                                      /* :454, :502 */
                         } else if (o->c.bcs[face] == 1) {
                             const double dn = orc_exact_dudn(coord(o, B, 0, i), coord(o, B, 1, j), coord(o, B, 2, k), dir);
-                            if (!up) b[ix] += 2 * dn / ds;                                   /* :480 */
-                            else     b[ix] -= 2 * dn / ds;                                   /* :527 */
+                            if (o->c.order_neumann == 1) {
+                                if (!up) b[ix] += dn / ds;                                   /* :475 */
+                                else     b[ix] -= dn / ds;                                   /* :522 */
+                            } else {
+                                if (!up) b[ix] += 2 * dn / ds;                               /* :479 */
+                                else     b[ix] -= 2 * dn / ds;                               /* :526 */
+                            }
                         }
                     }
         }
@@ -668,7 +682,7 @@ static int solve_bicgstab(orc_t* o) {
 }
 
 static int solve_cg(orc_t* o) {
-    /* baseCG.hpp:44-260 with isMainLoop = true, communicationON = true, orderNeumanBcs = 2 */
+    /* baseCG.hpp:44-260 with isMainLoop = true, communicationON = true */
     Ptrs P = ptrs_make(o);
     const double tol = o->c.tolerance;
     int iter = 0;
@@ -685,7 +699,9 @@ static int solve_cg(orc_t* o) {
     for (int r = 0; r < o->world; r++) memcpy(o->blk[r].p, o->blk[r].z, sizeof(double) * (size_t)o->blk[r].ntot);
     const double t0 = now_s();
     while (iter < o->c.max_iter) {
-        orc_halo_exchange(o, P.p);                                                /* :118-122; no Neumann reset for order 2 (:123-124) */
+        orc_halo_exchange(o, P.p);                                                /* :118-122 */
+        if (o->c.order_neumann == 1)                                              /* :123-124: only for order 1 */
+            for (int r = 0; r < o->world; r++) orc_reset_neumann(o, r, o->blk[r].p, 0, 1.0);
         for (int r = 0; r < o->world; r++) {
             Block* B = &o->blk[r];
             double s1 = 0.0, s2 = 0.0;
@@ -735,13 +751,72 @@ static int solve_cg(orc_t* o) {
         if (o->err_iter < tol) break;
     }
     o->iters = iter;
-    finish_solve(o, &P, t0, 0);
+    finish_solve(o, &P, t0, o->c.order_neumann == 1);                             /* :237-238 */
     ptrs_free(&P);
+    return 0;
+}
+
+static int solve_chebyshev(orc_t* o) {
+    /* chebyshevIteration.hpp:48-140 with isMainLoop = true, communicationON = true: cheb_max sweeps on the BC-adjusted
+     * copy of b with a halo exchange before every sweep; no normalisation (normFieldB_ stays 1), no residual history,
+     * x is written on the solver range only and neither de-normalised nor exchanged afterwards. */
+    const double theta = o->theta, delta = o->delta, sigma = o->sigma;
+    double rhoOld = 1 / sigma;
+    double rhoCurr = 1 / (2 * sigma - rhoOld);
+    double** bt = (double**)malloc(sizeof(double*) * (size_t)o->world);
+    double** ys = (double**)malloc(sizeof(double*) * (size_t)o->world);
+    for (int r = 0; r < o->world; r++) {
+        Block* B = &o->blk[r];
+        bt[r] = (double*)malloc(sizeof(double) * (size_t)B->ntot);
+        memcpy(bt[r], B->b, sizeof(double) * (size_t)B->ntot);                    /* :63-65 */
+        orc_adjust_b(o, r, B->x, bt[r]);                                          /* :66 */
+    }
+    orc_halo_exchange(o, bt);                                                     /* :69-73 */
+    for (int r = 0; r < o->world; r++) orc_reset_neumann(o, r, bt[r], 0, 1.0);    /* :74: fieldData = false -> plain mirror */
+    o->norm_b_report = 1.0;
+    const double t0 = now_s();
+    for (int r = 0; r < o->world; r++) {
+        Block* B = &o->blk[r];
+        FOR_SOLVER(B, i, j, k) {                                                  /* :79-91 */
+            const long q = i + B->sj * j + B->sk * k;
+            B->cz[q] = bt[r][q] / theta;
+            B->cy[q] = 2 * rhoCurr / delta * (2 * bt[r][q] + stencil(o, B, bt[r], i, j, k) / theta);
+        }
+    }
+    for (int c = 2; c <= o->c.cheb_max; c++) {                                    /* :94-116 */
+        rhoOld = rhoCurr;
+        rhoCurr = 1 / (2 * sigma - rhoOld);
+        for (int r = 0; r < o->world; r++) ys[r] = o->blk[r].cy;
+        orc_halo_exchange(o, ys);
+        for (int r = 0; r < o->world; r++) {
+            Block* B = &o->blk[r];
+            orc_reset_neumann(o, r, B->cy, 0, 1.0);
+            FOR_SOLVER(B, i, j, k) {
+                const long q = i + B->sj * j + B->sk * k;
+                B->cw[q] = rhoCurr * (2 * sigma * B->cy[q] + 2 / delta * (bt[r][q] + stencil(o, B, B->cy, i, j, k)) - rhoOld * B->cz[q]);
+            }
+            double* t = B->cz; B->cz = B->cy; B->cy = t;
+            t = B->cw; B->cw = B->cy; B->cy = t;
+        }
+    }
+    for (int r = 0; r < o->world; r++) {
+        Block* B = &o->blk[r];
+        FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; B->x[q] = (-1) * B->cw[q]; }   /* :118-128 */
+        free(bt[r]);
+    }
+    o->loop_seconds = now_s() - t0;
+    free(bt);
+    free(ys);
+    o->err_op = residual_norm(o, 1.0);                                            /* :134-135 */
+    o->err_iter = o->err_op;                                                      /* :136 */
+    o->iters = o->c.cheb_max;                                                     /* :137 */
+    o->hist[0] = o->err_op;
     return 0;
 }
 
 int orc_solve(orc_t* o) {
     o->norm_b = 1.0;
+    if (o->c.solver == ORC_SOLVER_CHEBYSHEV) return solve_chebyshev(o);
     return o->c.solver == ORC_SOLVER_CG ? solve_cg(o) : solve_bicgstab(o);
 }
 

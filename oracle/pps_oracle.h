@@ -20,7 +20,8 @@
 extern "C" {
 #endif
 
-enum { ORC_SOLVER_BICGSTAB = 0, ORC_SOLVER_CG = 1 };
+enum { ORC_SOLVER_BICGSTAB = 0, ORC_SOLVER_CG = 1,
+       ORC_SOLVER_CHEBYSHEV = 2 /* ChebyshevIteration<..., isMainLoop = true, communicationON, NoneSolver>: chebyshevIteration.hpp:48-140; cheb_max sweeps, no normalisation, no history */ };
 enum { ORC_PRECOND_NONE = 0,            /* T_NoneSolver,       inputParam.hpp:24 */
        ORC_PRECOND_CHEBYSHEV = 1,       /* T_Preconditioner2,  inputParam.hpp:28 */
        ORC_PRECOND_BICGSTAB_LOCAL = 2,  /* T_Preconditioner,   inputParam.hpp:31: BiCGSTAB, isMainLoop false, communicationOFF, NoneSolver inside */
@@ -42,6 +43,7 @@ typedef struct orc_config {
     double cheb_rescale_max; /* rescaleEigMax    solverSetup.hpp:39 */
     double precond_tolerance; /* tollPreconditionerSolver * tollScalingFactor   solverSetup.hpp:31 (nested Krylov preconditioners) */
     int precond_max_iter;     /* iterMaxPreconditioner   solverSetup.hpp:32 */
+    int order_neumann;        /* orderNeumanBcs: 2 (shipped) or 1   solverSetup.hpp:25 */
 } orc_config;
 
 typedef struct orc_block_info {
@@ -86,7 +88,7 @@ void orc_reset_neumann(const orc_t* o, int rank, double* field, int with_bc_valu
 void orc_adjust_b(const orc_t* o, int rank, const double* x, double* b);     /* iterativeSolverBase.hpp:429-534 */
 void orc_precondition(orc_t* o, double* const* X, double* const* B);         /* chebyshevIteration.hpp:48-140 or noneSolver.hpp:24-27 */
 
-/* the solver: BiCGSTAB.hpp:55-322 or baseCG.hpp:44-260 on orc_x / orc_b */
+/* the solver: BiCGSTAB.hpp:55-322, baseCG.hpp:44-260 or chebyshevIteration.hpp:48-140 (main loop) on orc_x / orc_b */
 int orc_solve(orc_t* o);
 int orc_iters(const orc_t* o);
 double orc_error_iteration(const orc_t* o);

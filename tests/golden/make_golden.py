@@ -7,7 +7,7 @@ and stores, per case, one compressed .npz with
     history       errorFromIterationHistory_[0..iters]      (BiCGSTAB.hpp:114-117,278-281)
     iters, norm_b, error_iteration, error_operator, tolerance
     x             final solution, data range only, assembled to the global grid (small cases)
-    np, nranks, ds, origin, bcs, solver, precond, max_iter, cheb_max    (the configuration)
+    np, nranks, ds, origin, bcs, solver, precond, max_iter, cheb_max, order_neumann, cheb_rescale_min/max    (the configuration)
 Only runnable where /root/reference exists (the build container); the fixtures travel.
 """
 from __future__ import annotations
@@ -47,6 +47,13 @@ CASES = [
     # nested Krylov preconditioners
     ("nb24", (1, 1, 1), True), ("nb24", (1, 1, 2), False), ("nb24", (3, 1, 2), False),
     ("nc24", (1, 1, 1), True), ("nc24", (2, 2, 1), False), ("nc24", (3, 1, 2), False),
+    # first-order Neumann closure (orderNeumanBcs = 1): BiCGSTAB, BiCGSTAB + Chebyshev, CG (which then resets ghosts)
+    ("o1m24", (1, 1, 1), True), ("o1m24", (1, 1, 2), False), ("o1m24", (3, 1, 2), False),
+    ("o1m24_cheb", (1, 1, 1), True), ("o1m24_cheb", (2, 2, 1), False),
+    ("o1cgm24", (1, 1, 1), True), ("o1cgm24", (1, 2, 2), False),
+    # Chebyshev iteration as main solver (fixed number of sweeps, no history)
+    ("chm24", (1, 1, 1), True), ("chm24", (1, 1, 2), True), ("chm24", (3, 2, 1), False),
+    ("chd32", (1, 1, 1), True), ("chd32", (2, 2, 2), False),
 ]
 
 
@@ -84,6 +91,9 @@ def run_case(name, ranks, store_x):
         r = subprocess.run([exe, *map(str, ranks), td], check=True, capture_output=True, text=True)
         s = read_summary(td + "/summary.txt")
         hist = np.fromfile(td + "/history.bin")
+        if c["solver"] == "cheb_main":
+            # the reference never fills errorFromIterationHistory_ in this mode: keep only the final residual
+            hist = np.array([float(s["error_operator"][0])])
         world = ranks[0] * ranks[1] * ranks[2]
         maxerr = [l for l in r.stdout.splitlines() if l.startswith("Max error local point")]
         out = dict(
@@ -94,6 +104,9 @@ def run_case(name, ranks, store_x):
             origin=np.array(c["origin"], dtype=float), bcs=np.array(c["bcs"]),
             solver=c["solver"].split("_")[0], precond=c["solver"].split("_")[1], cheb_max=c["cheb_max"],
             max_point_error=float(maxerr[0].split()[4]) if maxerr else np.nan,
+            order_neumann=c.get("order_neumann", 2),
+            cheb_rescale_min=500.0 if c.get("rescale_min") is None else float(c["rescale_min"]),
+            cheb_rescale_max=1 - 1e-4 if c.get("rescale_max") is None else float(c["rescale_max"]),
         )
         if store_x:
             out["x"] = assemble(td, world, c["np"])

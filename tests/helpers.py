@@ -22,13 +22,17 @@ def load_golden(name):
 
 
 def oracle_config_from_golden(g, nranks=None, max_iter=None, tolerance=None):
-    solver = po.SOLVER_CG if str(g["solver"]) == "cg" else po.SOLVER_BICGSTAB
+    solver = {"cg": po.SOLVER_CG, "cheb": po.SOLVER_CHEBYSHEV}.get(str(g["solver"]), po.SOLVER_BICGSTAB)
+    extra = {}
+    if "order_neumann" in g:   # fixtures written before these knobs existed are order 2 with the shipped rescaling
+        extra = dict(order_neumann=int(g["order_neumann"]), cheb_rescale_min=float(g["cheb_rescale_min"]),
+                     cheb_rescale_max=float(g["cheb_rescale_max"]))
     precond = {"cheb": po.PRECOND_CHEBYSHEV, "bicgloc": po.PRECOND_BICGSTAB_LOCAL, "cgcheb": po.PRECOND_CG_CHEB_LOCAL}.get(str(g["precond"]), po.PRECOND_NONE)
     return po.make_config(
         np_=[int(v) for v in g["np"]], nranks=[int(v) for v in (g["nranks"] if nranks is None else nranks)],
         ds=[float(v) for v in g["ds"]], origin=[float(v) for v in g["origin"]], bcs=[int(v) for v in g["bcs"]],
         solver=solver, precond=precond, tolerance=float(g["tolerance"]) if tolerance is None else tolerance,
-        max_iter=int(g["max_iter"]) if max_iter is None else max_iter, cheb_max=int(g["cheb_max"]))
+        max_iter=int(g["max_iter"]) if max_iter is None else max_iter, cheb_max=int(g["cheb_max"]), **extra)
 
 
 def assemble_global(fields, blocks, npglobal):

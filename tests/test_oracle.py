@@ -13,7 +13,7 @@ from oracle import pyoracle as po
 from tests import helpers as H
 
 FAST_CASES = [n for n in H.golden_names()
-              if n.split("_")[0] in ("d16", "d32", "m24", "n24", "cg32", "cgm24", "m32", "nb24", "nc24") or n in ("d64_111", "d64_cheb_111", "d64_118", "d64_cheb_118")]
+              if n.split("_")[0] in ("d16", "d32", "m24", "n24", "cg32", "cgm24", "m32", "nb24", "nc24", "o1m24", "o1cgm24", "chm24", "chd32") or n in ("d64_111", "d64_cheb_111", "d64_118", "d64_cheb_118")]
 SLOW_CASES = [n for n in H.golden_names() if n not in FAST_CASES]
 
 
@@ -24,8 +24,12 @@ def _run_case(name):
     o.solve()
     assert o.iters == int(g["iters"])
     h = o.history()
-    assert h.shape == g["history"].shape
-    assert np.array_equal(h, g["history"]), "residual history differs from the reference"
+    if str(g["solver"]) == "cheb":
+        # Chebyshev as main solver keeps no history (chebyshevIteration.hpp:132-139): the fixture holds the final residual only
+        assert h[0] == g["history"][0]
+    else:
+        assert h.shape == g["history"].shape
+        assert np.array_equal(h, g["history"]), "residual history differs from the reference"
     assert o.norm_b == float(g["norm_b"])
     assert o.error_operator == float(g["error_operator"])
     assert o.error_iteration == float(g["error_iteration"])
