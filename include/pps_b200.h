@@ -36,11 +36,15 @@ extern "C" {
 #define PPS_UNIQUE_ID_BYTES 128
 
 /* main solver: T_Solver of inputParam.hpp:33 */
-enum { PPS_SOLVER_BICGSTAB = 0, /* BiCGSTAB.hpp  */
-       PPS_SOLVER_CG = 1        /* baseCG.hpp    */ };
-/* preconditioner slot: T_NoneSolver / T_Preconditioner2 of inputParam.hpp:24,28 */
-enum { PPS_PRECOND_NONE = 0,      /* noneSolver.hpp */
-       PPS_PRECOND_CHEBYSHEV = 1  /* chebyshevIteration.hpp, communicationOFF (block-Jacobi) */ };
+enum { PPS_SOLVER_BICGSTAB = 0,  /* BiCGSTAB.hpp  */
+       PPS_SOLVER_CG = 1,        /* baseCG.hpp    */
+       PPS_SOLVER_CHEBYSHEV = 2  /* chebyshevIteration.hpp:48-140 with isMainLoop = true, communicationON: cheb_max_iter sweeps,
+                                    no normalisation, no residual history (only the final ||b - A x||); precond must be NONE */ };
+/* preconditioner slot: T_NoneSolver / T_Preconditioner2 / T_Preconditioner / T_Preconditioner3 of inputParam.hpp:24-31 */
+enum { PPS_PRECOND_NONE = 0,            /* noneSolver.hpp */
+       PPS_PRECOND_CHEBYSHEV = 1,       /* chebyshevIteration.hpp, communicationOFF (block-Jacobi) */
+       PPS_PRECOND_BICGSTAB_LOCAL = 2,  /* BiCGSTAB<.., isMainLoop false, communicationOFF, NoneSolver>   inputParam.hpp:31 */
+       PPS_PRECOND_CG_CHEB_LOCAL = 3    /* BaseCG<.., isMainLoop false, communicationOFF, Chebyshev>      inputParam.hpp:29 */ };
 /* arithmetic of the operator: FAST = precomputed 1/ds^2 and FMA; PARITY = the reference's
  * expression order with IEEE division and no contraction (bit-identical per point to the
  * g++ build of matrixFreeOperatorA.hpp:33-38; slower, for kernel parity tests) */
@@ -67,12 +71,14 @@ typedef struct pps_config {
     double cheb_epsilon;      /* epsilon, solverSetup.hpp:37 */
     double cheb_rescale_min;  /* rescaleEigMin, solverSetup.hpp:38 */
     double cheb_rescale_max;  /* rescaleEigMax, solverSetup.hpp:39 */
-    int order_neumann;        /* orderNeumanBcs, solverSetup.hpp:25 (2) */
+    int order_neumann;        /* orderNeumanBcs, solverSetup.hpp:25: 2 (shipped) or 1 */
     int arithmetic;           /* PPS_ARITH_* */
     int fusion;               /* PPS_FUSE_* */
     int device;               /* CUDA device ordinal, -1 = current */
     int flags;                /* PPS_FLAG_* */
-    int reserved[7];
+    int precond_max_iter;     /* iterMaxPreconditioner, solverSetup.hpp:32 (nested Krylov preconditioners); 0 = 150 */
+    double precond_tolerance; /* tollPreconditionerSolver * tollScalingFactor, solverSetup.hpp:31; 0 = 1e4 * 1e-10 */
+    int reserved[4];
 } pps_config;
 
 /* pps_config.flags */
@@ -132,6 +138,9 @@ int pps_get_solution(pps_handle* h, int rank, double* x_host);
 int pps_get_rhs(pps_handle* h, int rank, double* b_host);
 
 int pps_get_iterations(const pps_handle* h);                 /* getNumIterationFinal, iterativeSolverBase.hpp:422-425 */
+/* iterations of a nested Krylov preconditioner during the last solve, summed over its calls and over the local blocks
+ * (getNumIterationPreconditionerFinal of the alpaka tree, iterativeSolverBaseAlpaka.hpp:615-618); 0 for the others */
+long long pps_get_preconditioner_iterations(const pps_handle* h);
 double pps_get_error_iteration(const pps_handle* h);         /* getErrorFromIteration,  :414-417 */
 double pps_get_error_operator(const pps_handle* h);          /* getErrorComputeOperator, :418-421 */
 double pps_get_norm_b(const pps_handle* h);                  /* normFieldB_ as printed at BiCGSTAB.hpp:108 */

@@ -38,6 +38,8 @@ struct StackInfo {
     int precond_kind;    // PPS_PRECOND_* when used in the preconditioner slot, -1 = not implemented there
     int iterations;      // maxIteration template argument
     bool communication;  // communicationON template argument
+    int tolerance = 0;         // tolerance template argument (times tollScalingFactor), used by nested Krylov preconditioners
+    int inner_iterations = 0;  // maxIteration of the Chebyshev iteration inside a nested CG (T_Preconditioner3, inputParam.hpp:29)
 };
 
 template <int DIM, typename T_data, int maxIteration>
@@ -50,7 +52,15 @@ class SolverAdapter {
         const auto nr = blockGrid.getNranks();
         nranksTot_ = nr[0] * nr[1] * nr[2];
         if (self.solver_kind < 0) { std::cerr << "Error: " << name << " is not available as the main solver" << std::endl; std::exit(-1); }
-        if (precond.precond_kind < 0) { std::cerr << "Error: nested Krylov preconditioners are not implemented on the B200 path" << std::endl; std::exit(-1); }
+        if (precond.precond_kind < 0) {
+            std::cerr << "Error: this preconditioner stack is not implemented on the B200 path (available: NoneSolver, ChebyshevIteration, "
+                         "BiCGSTAB<.., false, communicationOFF, NoneSolver>, BaseCG<.., false, communicationOFF, ChebyshevIteration>)" << std::endl;
+            std::exit(-1);
+        }
+        if (self.solver_kind == PPS_SOLVER_CHEBYSHEV && precond.precond_kind != PPS_PRECOND_NONE) {
+            std::cerr << "Error: ChebyshevIteration as main solver ignores its preconditioner slot: use NoneSolver there" << std::endl;
+            std::exit(-1);
+        }
         if (precond.precond_kind == PPS_PRECOND_CHEBYSHEV && precond.communication) {
             std::cerr << "Error: the Chebyshev preconditioner is implemented with communicationOFF (block-Jacobi) only" << std::endl;
             std::exit(-1);
@@ -71,6 +81,13 @@ class SolverAdapter {
         c.tolerance = static_cast<T_data>(tolerance) * tollScalingFactor;   // BiCGSTAB.hpp:22
         c.max_iter = maxIteration;
         c.cheb_max_iter = precond.precond_kind == PPS_PRECOND_CHEBYSHEV ? precond.iterations : chebyshevMax;
+        if (self.solver_kind == PPS_SOLVER_CHEBYSHEV) c.cheb_max_iter = maxIteration;                 // chebyshevIteration.hpp:94,137
+        if (precond.precond_kind == PPS_PRECOND_CG_CHEB_LOCAL) c.cheb_max_iter = precond.inner_iterations;
+        nested_ = precond.precond_kind == PPS_PRECOND_BICGSTAB_LOCAL || precond.precond_kind == PPS_PRECOND_CG_CHEB_LOCAL;
+        if (nested_) {
+            c.precond_tolerance = static_cast<T_data>(precond.tolerance) * tollScalingFactor;         // BiCGSTAB.hpp:22 of the nested solver
+            c.precond_max_iter = precond.iterations;
+        }
         c.cheb_epsilon = epsilon;
         c.cheb_rescale_min = rescaleEigMin;
         c.cheb_rescale_max = rescaleEigMax;
@@ -158,7 +175,8 @@ class SolverAdapter {
         errorComputeOperator_ = pps_get_error_operator(h_);
         normFieldB_ = pps_get_norm_b(h_);
         durationSolver_ = std::chrono::duration<double>(pps_get_loop_seconds(h_));
-        if (rank_ == 0) report();
+        precondTotal_ = pps_get_preconditioner_iterations(h_);
+        if (rank_ == 0 && cfg_.solver != PPS_SOLVER_CHEBYSHEV) report();   // the Chebyshev main loop prints nothing (chebyshevIteration.hpp:48-140)
     }
 
     // iterativeSolverBase.hpp:283-408: per-rank sum and max of |x - u_exact| on the data range, gathered, two lines on rank 0
@@ -202,7 +220,9 @@ class SolverAdapter {
     T_data getErrorComputeOperator() const { return errorComputeOperator_; }
     int getNumIterationFinal() const { return numIterationFinal_; }
     // extras of the alpaka tree (iterativeSolverBaseAlpaka.hpp:615-638)
-    int getNumIterationPreconditionerFinal() const { return 2 * precondIterations_ * numIterationFinal_; }
+    int getNumIterationPreconditionerFinal() const {
+        return nested_ ? static_cast<int>(precondTotal_) : 2 * precondIterations_ * numIterationFinal_;
+    }
     void writeResidualHistory() const {
         const std::vector<T_data> hst = getResidualHistory();
         write_residual_history("residualHistory.txt", durationSolver_.count(), numIterationFinal_, getNumIterationPreconditionerFinal(),
@@ -254,7 +274,8 @@ class SolverAdapter {
     const ExactSolutionAndBCs<DIM, T_data>& exact_;
     const char* name_;
     int rank_ = 0, nranksTot_ = 1, precondIterations_ = 0;
-    bool shared_ = false;
+    bool shared_ = false, nested_ = false;
+    long long precondTotal_ = 0;
     pps_config cfg_{};
     pps_handle* h_ = nullptr;
     T_data normFieldB_ = 1, errorFromIteration_ = -1, errorComputeOperator_ = -1;

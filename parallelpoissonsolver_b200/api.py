@@ -7,8 +7,8 @@ import os
 
 import numpy as np
 
-SOLVER_BICGSTAB, SOLVER_CG = 0, 1
-PRECOND_NONE, PRECOND_CHEBYSHEV = 0, 1
+SOLVER_BICGSTAB, SOLVER_CG, SOLVER_CHEBYSHEV = 0, 1, 2
+PRECOND_NONE, PRECOND_CHEBYSHEV, PRECOND_BICGSTAB_LOCAL, PRECOND_CG_CHEB_LOCAL = 0, 1, 2, 3
 ARITH_FAST, ARITH_PARITY = 0, 1
 FUSE_AUTO, FUSE_SPLIT, FUSE_FULL = 0, 1, 2
 FLAG_OPERATOR_ONLY = 1
@@ -29,7 +29,8 @@ class Config(C.Structure):
         ("solver", C.c_int), ("precond", C.c_int), ("tolerance", C.c_double), ("max_iter", C.c_int),
         ("cheb_max_iter", C.c_int), ("cheb_epsilon", C.c_double), ("cheb_rescale_min", C.c_double),
         ("cheb_rescale_max", C.c_double), ("order_neumann", C.c_int), ("arithmetic", C.c_int), ("fusion", C.c_int),
-        ("device", C.c_int), ("flags", C.c_int), ("reserved", C.c_int * 7),
+        ("device", C.c_int), ("flags", C.c_int), ("precond_max_iter", C.c_int), ("precond_tolerance", C.c_double),
+        ("reserved", C.c_int * 4),
     ]
 
 
@@ -78,6 +79,8 @@ def load_library():
     L.pps_get_solution.argtypes = [P, C.c_int, C.c_void_p]
     L.pps_get_rhs.argtypes = [P, C.c_int, C.c_void_p]
     L.pps_get_iterations.argtypes = [P]
+    L.pps_get_preconditioner_iterations.argtypes = [P]
+    L.pps_get_preconditioner_iterations.restype = C.c_longlong
     for f in ("pps_get_error_iteration", "pps_get_error_operator", "pps_get_norm_b", "pps_get_solver_seconds",
               "pps_get_loop_seconds"):
         getattr(L, f).restype = C.c_double
@@ -108,7 +111,7 @@ def default_config() -> Config:
 def make_config(npglobal, nranks=(1, 1, 1), ds=(0.1, 0.1, 0.1), origin=(0.0, 0.0, 0.0), bcs=(0, 0, 0, 0, 0, 0),
                 solver=SOLVER_BICGSTAB, precond=PRECOND_NONE, tolerance=1e-8, max_iter=1700, cheb_max_iter=11,
                 cheb_epsilon=1e-4, cheb_rescale_min=500.0, cheb_rescale_max=1 - 1e-4, arithmetic=ARITH_FAST,
-                fusion=FUSE_AUTO, device=-1, flags=0) -> Config:
+                fusion=FUSE_AUTO, device=-1, flags=0, order_neumann=2, precond_tolerance=1e4 * 1e-10, precond_max_iter=150) -> Config:
     c = Config()
     c.abi_version = ABI_VERSION
     c.dim = 3
@@ -122,7 +125,8 @@ def make_config(npglobal, nranks=(1, 1, 1), ds=(0.1, 0.1, 0.1), origin=(0.0, 0.0
     c.tolerance, c.max_iter = float(tolerance), int(max_iter)
     c.cheb_max_iter, c.cheb_epsilon = int(cheb_max_iter), float(cheb_epsilon)
     c.cheb_rescale_min, c.cheb_rescale_max = float(cheb_rescale_min), float(cheb_rescale_max)
-    c.order_neumann = 2
+    c.order_neumann = int(order_neumann)
+    c.precond_tolerance, c.precond_max_iter = float(precond_tolerance), int(precond_max_iter)
     c.arithmetic, c.fusion, c.device = arithmetic, fusion, device
     c.flags = flags
     return c
@@ -235,6 +239,11 @@ class PoissonSolver:
     @property
     def iterations(self) -> int:
         return self.L.pps_get_iterations(self.h)
+
+    @property
+    def preconditioner_iterations(self) -> int:
+        """iterations of a nested Krylov preconditioner during the last solve (summed over calls and local blocks)"""
+        return self.L.pps_get_preconditioner_iterations(self.h)
 
     @property
     def error_iteration(self) -> float:

@@ -624,6 +624,34 @@ __global__ void scale_kernel(double* __restrict__ a, double* __restrict__ b, lon
     }
 }
 
+// ---- nested (block-local) Krylov preconditioners: BiCGSTAB / BaseCG with isMainLoop = false, communicationOFF ----
+// start values of a nested solve (BiCGSTAB.hpp:60-66,127; baseCG.hpp:49-66).  When the OUTER solve has already converged the
+// nested solve starts `done`, so every kernel of it returns at once, and entry 0 of its history tells the host to stop.
+__global__ void inner_begin_kernel(Ctl* c, const Ctl* outer, double tol, int max_iter) {
+    c->rho0 = 1; c->alpha = 1; c->omega = 1; c->beta = 1; c->err = -1; c->rz = 1; c->norm_b = 1; c->tol = tol;
+    for (int q = 0; q < 8; q++) c->sums[q] = 0;
+    c->iter = 0; c->max_iter = max_iter; c->pad = 0;
+    c->done = (outer != nullptr && outer->done) ? 1 : 0;
+    c->hist_err[0] = c->done ? -1.0 : 1e300;
+}
+// a, b /= (mode 0) or *= (mode 1) the norm the NESTED solve normalised with, over every entry (iterativeSolverBase.hpp:227-231,
+// BiCGSTAB.hpp:310-314); skipped when the OUTER solve is done.  a may be null.
+__global__ void inner_scale_kernel(double* __restrict__ a, double* __restrict__ b, long long n, const Ctl* inner, const Ctl* outer,
+                                   int mode) {
+    if (outer != nullptr && outer->done) return;
+    const double s = inner->norm_b;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (mode == 0) {
+            if (a != nullptr) a[i] = __ddiv_rn(a[i], s);
+            b[i] = __ddiv_rn(b[i], s);
+        } else {
+            if (a != nullptr) a[i] = __dmul_rn(a[i], s);
+            b[i] = __dmul_rn(b[i], s);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // face kernels: O(N^2) work on one face of a block
 // ------------------------------------------------------------------------------------------------
@@ -637,7 +665,8 @@ struct FaceGeom {
 
 // resetNeumanBCs (iterativeSolverBase.hpp:62-169), orderNeumanBcs = 2:
 //   ghost(A) = mirror(B)                                  helper fields
-//   ghost(A) = mirror(B) -/+ 2 ds dudn / norm_b           solution field in the main loop (:105, :153)
+//   ghost(A) = mirror(B) -/+ 2 ds dudn / norm_b           solution field in the main loop (:100, :148)
+// orderNeumanBcs == 1 (:92-95, :105-108, :140-143, :153-156): the host passes the boundary plane as B and ds as `two_ds`
 __global__ void neumann_ghost_kernel(double* __restrict__ f, FaceGeom g, const double* __restrict__ dudn, double two_ds,
                                      int upper, const Ctl* ctl, int ignore_done) {
     if (!ignore_done && ctl != nullptr && ctl->done) return;
@@ -684,9 +713,10 @@ __global__ void neumann_ghost_batch_kernel(double* __restrict__ f, GhostBatch ba
 
 // adjustFieldBForDirichletNeumanBCs (iterativeSolverBase.hpp:429-534), one face:
 //   Dirichlet: b(A = first interior plane) -= x(B = boundary plane) / ds^2        (:454, :502)
-//   Neumann:   b(A = boundary plane)      +/-= 2 dudn / ds                         (:480, :527)
+//   Neumann:   b(A = boundary plane)      +/-= nfac dudn / ds                      (:475-480, :522-527)
+//              nfac = 2 for orderNeumanBcs == 2, 1 for orderNeumanBcs == 1 (1 * dudn is exact, so both are the reference's bits)
 __global__ void adjust_b_kernel(double* __restrict__ b, const double* __restrict__ x, FaceGeom g,
-                                const double* __restrict__ dudn, double ds, int neumann, int upper) {
+                                const double* __restrict__ dudn, double ds, int neumann, int upper, double nfac) {
     const long long n = static_cast<long long>(g.nu) * g.nv;
     for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < n;
          t += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -694,7 +724,7 @@ __global__ void adjust_b_kernel(double* __restrict__ b, const double* __restrict
         if (!neumann) {
             b[g.base_a + off] = __dsub_rn(b[g.base_a + off], __ddiv_rn(x[g.base_b + off], __dmul_rn(ds, ds)));
         } else {
-            const double c = __ddiv_rn(__dmul_rn(2.0, dudn[t]), ds);
+            const double c = __ddiv_rn(__dmul_rn(nfac, dudn[t]), ds);
             b[g.base_a + off] = upper ? __dsub_rn(b[g.base_a + off], c) : __dadd_rn(b[g.base_a + off], c);
         }
     }

@@ -80,6 +80,10 @@ struct Block {
     double *cy = nullptr, *cz = nullptr, *cw = nullptr;
     double *x_saved = nullptr, *b_saved = nullptr;
     double *p2 = nullptr, *v2 = nullptr, *s = nullptr;   // PPS_FUSE_FULL: ping-pong p / v, separate s
+    // nested (block-local) Krylov preconditioner: its own work vectors, control block and residual history
+    double *ip = nullptr, *ir = nullptr, *ir0 = nullptr, *iv = nullptr, *it = nullptr, *iz = nullptr;
+    Ctl* ictl = nullptr;                 // device
+    double* ihist_host = nullptr;        // host-mapped, 4 x (precond_max_iter + 2): err, alpha, omega, rho
     double* dudn[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* sendbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* recvbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -108,7 +112,13 @@ struct pps_handle {
     std::vector<Block> blocks;
     cudaStream_t stream = nullptr;
     Ctl* ctl = nullptr;         // device
+    Ctl* actl = nullptr;        // control block the launchers hand to the kernels: ctl, or a block's ictl inside a nested solve
+    bool local_reduce = false;  // nested solve: reductions stay on this block (no allreduce), the last CTA applies the scalar op
     Ctl ctl_host{};
+    int precond_max_iter = 150;          // iterMaxPreconditioner, solverSetup.hpp:32
+    double precond_tolerance = 1e-6;     // tollPreconditionerSolver * tollScalingFactor, solverSetup.hpp:31
+    long long precond_iters = 0;         // nested iterations of the last solve, summed over calls and local blocks
+    std::vector<cudaEvent_t> inner_events;
     double* hist_host[4] = {nullptr, nullptr, nullptr, nullptr};   // host-mapped
     double* hist_dev[4] = {nullptr, nullptr, nullptr, nullptr};
     int hist_len = 0;
@@ -282,10 +292,10 @@ static RedCtx make_red(pps_handle* h, int nacc, unsigned int total, unsigned int
     r.total_ctas = total;
     r.cta_offset = offset;
     r.nacc = nacc;
-    r.op = (h->world > 1) ? static_cast<int>(OP_NONE) : op;
-    r.ctl = h->ctl;
+    r.op = (h->world > 1 && !h->local_reduce) ? static_cast<int>(OP_NONE) : op;
+    r.ctl = h->actl;
     r.pr = PeerReduce{nullptr, nullptr, 0, 0, 0};
-    if (h->ar_p2p && nacc > 0 && op != OP_NONE) {
+    if (h->ar_p2p && !h->local_reduce && nacc > 0 && op != OP_NONE) {
         // the allreduce happens inside the reducing kernel: every launch that feeds this reduction carries the same epoch
         // (finish_reduction bumps it once the launches of the reduction have been issued)
         r.op = op;
@@ -297,7 +307,7 @@ static RedCtx make_red(pps_handle* h, int nacc, unsigned int total, unsigned int
 
 // after a fused reduction: allreduce the raw sums over NVLink and apply the scalar update (world > 1 only)
 static void finish_reduction(pps_handle* h, int nacc, int op, bool ignore_done) {
-    if (h->world == 1) return;
+    if (h->world == 1 || h->local_reduce) return;
     if (h->ar_p2p && op != OP_NONE) {
         h->ar_epoch++;   // done in-kernel (PeerReduce); next reduction, next epoch
         return;
@@ -369,7 +379,7 @@ static void launch_tma_pre(pps_handle* h, int kc, const Block& b, const Box& box
     const CUtensorMap& a0 = Epi::NAUX > 0 ? tensor_map(h, b, epi.aux(0), BY, true) : i0;
     const CUtensorMap& a1 = Epi::NAUX > 1 ? tensor_map(h, b, epi.aux(1), BY, true) : i0;
     kern<<<t.grid, t.block, smem, h->launch_stream>>>(i0, i1, i2, a0, a1, b.g.dims, box, h->coef, t.zchunk, t.org, pre, epi, red,
-                                                       check_done ? h->ctl : nullptr);
+                                                       check_done ? h->actl : nullptr);
     check_launch(kKernelNames[kc]);
     ls.count(1);
 }
@@ -378,7 +388,7 @@ template <class Epi>
 static void launch_stencil(pps_handle* h, int kc, const Block& b, const double* u, const Box& box, const Epi& epi,
                            const RedCtx& red, const Tiling& t, bool check_done) {
     LaunchScope ls(h, kc);
-    const Ctl* ctl = check_done ? h->ctl : nullptr;
+    const Ctl* ctl = check_done ? h->actl : nullptr;
     if (h->stencil_impl == 1) {
         if (h->by_tma == 16) {
             if (h->parity) launch_tma_inst<16, 4, true>(h, b, u, box, epi, red, t, ctl);
@@ -404,7 +414,7 @@ static void launch_pointwise(pps_handle* h, int kc, const Block& b, const Box& b
     LaunchScope ls(h, kc);
     // pointwise ops read their scalars from ctl in begin(), so they always get ctl and therefore always honour ctl->done;
     // they are only launched inside the iteration or during set-up, where done == 0 (`check_done` documents the call site)
-    const Ctl* ctl = h->ctl;
+    const Ctl* ctl = h->actl;
     (void)check_done;
     if (h->by == 4) pointwise_kernel<4, Op><<<t.grid, t.block, 0, h->stream>>>(b.g.dims, box, t.zchunk, t.org, op, red, ctl);
     else            pointwise_kernel<8, Op><<<t.grid, t.block, 0, h->stream>>>(b.g.dims, box, t.zchunk, t.org, op, red, ctl);
@@ -444,6 +454,8 @@ static double* sel_x(Block& b) { return b.x; }
 static double* sel_p(Block& b) { return b.p; }
 static double* sel_mp(Block& b) { return b.mp; }
 static double* sel_z(Block& b) { return b.z; }
+static double* sel_t(Block& b) { return b.t; }
+static double* sel_cy(Block& b) { return b.cy; }
 
 // CommunicatorMPI::operator() + waitAllandCheckRcv (communicationMPI.hpp:51-316).  `on_halo_stream`: issue the
 // exchange on the high-priority halo stream with its own communicator (overlap with interior compute).
@@ -641,6 +653,9 @@ static void neumann_ghosts(pps_handle* h, Block& b, double* field, bool with_val
     for (int f = 0; f < 6; f++) any = any || (b.g.hb[f] && h->cfg.bcs_type[f] == 1);
     if (!any) return;
     LaunchScope ls(h, KC_GHOST);
+    // orderNeumanBcs == 2: ghost = first interior plane -/+ 2 ds g; == 1: ghost = boundary plane -/+ ds g  (iterativeSolverBase.hpp:92-108)
+    const int src_plane = h->cfg.order_neumann == 1 ? 1 : 2;
+    const double step = h->cfg.order_neumann == 1 ? 1.0 : 2.0;
     if (h->batch_ghosts) {
         GhostBatch batch{};
         int blocks = 1;
@@ -649,26 +664,26 @@ static void neumann_ghosts(pps_handle* h, Block& b, double* field, bool with_val
             if (with_value && b.dudn[f] == nullptr)
                 throw std::runtime_error("Neumann face " + std::to_string(f) + " has no du/dn values: call pps_set_neumann_face first");
             const int q = batch.count++;
-            batch.g[q] = face_geom(b.g, f, 0, 2);
+            batch.g[q] = face_geom(b.g, f, 0, src_plane);
             batch.dudn[q] = with_value ? b.dudn[f] : nullptr;
-            batch.two_ds[q] = 2 * h->cfg.ds[f / 2];
+            batch.two_ds[q] = step * h->cfg.ds[f / 2];
             batch.upper[q] = f % 2;
             blocks = std::max(blocks, face_blocks(batch.g[q]));
         }
-        neumann_ghost_batch_kernel<<<dim3(blocks, batch.count), 256, 0, h->stream>>>(field, batch, h->ctl, check_done ? 0 : 1);
+        neumann_ghost_batch_kernel<<<dim3(blocks, batch.count), 256, 0, h->stream>>>(field, batch, h->actl, check_done ? 0 : 1);
         ls.count(1);
         check_launch("neumann_ghost_batch");
         return;
     }
     for (int f = 0; f < 6; f++) {
         if (!(b.g.hb[f] && h->cfg.bcs_type[f] == 1)) continue;
-        FaceGeom g = face_geom(b.g, f, 0, 2);
-        const double two_ds = 2 * h->cfg.ds[f / 2];
+        FaceGeom g = face_geom(b.g, f, 0, src_plane);
+        const double two_ds = step * h->cfg.ds[f / 2];
         if (with_value && b.dudn[f] == nullptr)
             throw std::runtime_error("Neumann face " + std::to_string(f) + " of rank " + std::to_string(b.g.rank) +
                                      " has no du/dn values: call pps_set_neumann_face first");
         neumann_ghost_kernel<<<face_blocks(g), 256, 0, h->stream>>>(field, g, with_value ? b.dudn[f] : nullptr, two_ds,
-                                                                    f % 2, h->ctl, check_done ? 0 : 1);
+                                                                    f % 2, h->actl, check_done ? 0 : 1);
         ls.count(1);
     }
     check_launch("neumann_ghost");
@@ -683,7 +698,8 @@ static void adjust_b(pps_handle* h, Block& b, double* bcopy) {
         FaceGeom g = neumann ? face_geom(b.g, f, 1, 1) : face_geom(b.g, f, 2, 1);
         if (neumann && b.dudn[f] == nullptr)
             throw std::runtime_error("Neumann face " + std::to_string(f) + " has no du/dn values");
-        adjust_b_kernel<<<face_blocks(g), 256, 0, h->stream>>>(bcopy, b.x, g, b.dudn[f], h->cfg.ds[f / 2], neumann, f % 2);
+        adjust_b_kernel<<<face_blocks(g), 256, 0, h->stream>>>(bcopy, b.x, g, b.dudn[f], h->cfg.ds[f / 2], neumann, f % 2,
+                                                               h->cfg.order_neumann == 1 ? 1.0 : 2.0);
         ls.count(1);
     }
     check_launch("adjust_b");
@@ -702,8 +718,7 @@ static unsigned int total_ctas(pps_handle* h, bool stencil) {
 // CHEBYSHEV: chebyshevIteration.hpp:48-140 with communicationOFF; the iterates y_{n-1}, y_n the reference
 // computes and discards (its pointer swaps leave y_{n-2} in fieldW, :114-125) are not computed and the
 // final X = -W is folded into the last live sweep -- bit-identical output, 35 instead of 45 vector passes.
-static void precondition(pps_handle* h, Block& b, double* X, double* B, bool check_done) {
-    if (h->cfg.precond == PPS_PRECOND_NONE) return;
+static void chebyshev_local(pps_handle* h, Block& b, double* X, double* B, bool check_done) {
     const int m = h->cfg.cheb_max_iter;
     const Box box = b.g.solver_box();
     const Tiling t = make_tiling(h, b.g, box, true);
@@ -738,6 +753,157 @@ static void precondition(pps_handle* h, Block& b, double* X, double* B, bool che
         // swap(Z, Y); swap(W, Y)  (chebyshevIteration.hpp:114-115)
         double* tmp = Z; Z = Y; Y = tmp;
         tmp = W; W = Y; Y = tmp;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Nested Krylov preconditioners (inputParam.hpp:29,31): BiCGSTAB<.., isMainLoop = false, communicationOFF, NoneSolver> and
+// BaseCG<.., isMainLoop = false, communicationOFF, ChebyshevIteration> in the preconditioner slot.  Everything is local to the
+// block: no face exchange, no allreduce, Neumann ghosts are plain mirrors.  The nested solve has its own device control block
+// (b.ictl): the operator / axpy kernels of the main loop are reused with it as the active control block, so its scalars,
+// its `done` flag and its residual history live on the device exactly like the outer ones.  The host looks at the nested
+// history `lag` iterations late to stop launching; when the OUTER solve has converged the nested one starts `done`.
+// Reference quirks kept: X is zeroed and B is divided by its own norm and multiplied back at the end, so the caller's
+// vector changes in its last bits (BiCGSTAB.hpp:96,310-314); when the start residual is already below the tolerance the
+// solve returns WITHOUT multiplying back (:118-122).
+// ------------------------------------------------------------------------------------------------
+static void zero_field(pps_handle* h, const Block& b, double* f);
+static void copy_field(pps_handle* h, const Block& b, double* dst, const double* src);
+
+struct InnerScope {
+    pps_handle* h;
+    Ctl* saved;
+    bool saved_local;
+    InnerScope(pps_handle* h_, Ctl* c) : h(h_), saved(h_->actl), saved_local(h_->local_reduce) {
+        h->actl = c;
+        h->local_reduce = true;
+    }
+    ~InnerScope() {
+        h->actl = saved;
+        h->local_reduce = saved_local;
+    }
+};
+
+// X = 0; B /= ||B||_solver; r = B - A X, ||r||.  Returns false when the nested solve must not iterate (start residual below the
+// tolerance, or the outer solve is done).     normalizeProblemToFieldBNorm<false,false> + computeErrorOperatorA<false,false>
+static bool nested_start(pps_handle* h, Block& b, double* X, double* B, double* r, bool check_done) {
+    const Box box = b.g.solver_box();
+    const Tiling tp = make_tiling(h, b.g, box, false);
+    const Tiling ts = make_tiling(h, b.g, box, true);
+    {
+        LaunchScope ls(h, KC_SETUP);
+        inner_begin_kernel<<<1, 1, 0, h->stream>>>(b.ictl, check_done ? h->ctl : nullptr, h->precond_tolerance, h->precond_max_iter);
+        ls.count(1);
+    }
+    zero_field(h, b, X);                                                          // BiCGSTAB.hpp:96 / baseCG.hpp:79
+    launch_pointwise(h, KC_DOT, b, box, OpDot{B, nullptr}, make_red(h, 2, tp.ctas(), 0, OP_NORM_B), tp, true);
+    {
+        LaunchScope ls(h, KC_SETUP);
+        // X is all zeros: 0 / norm = 0, only B needs the division
+        inner_scale_kernel<<<148 * 8, 256, 0, h->stream>>>(nullptr, B, b.g.dims.total, b.ictl, check_done ? h->ctl : nullptr, 0);
+        ls.count(1);
+        check_launch("inner_scale");
+    }
+    neumann_ghosts(h, b, X, false, true);
+    if (h->parity) launch_stencil(h, KC_RESIDUAL, b, X, box, EpiResidual<true>{r, B}, make_red(h, 1, ts.ctas(), 0, OP_RESIDUAL0), ts, true);
+    else           launch_stencil(h, KC_RESIDUAL, b, X, box, EpiResidual<false>{r, B}, make_red(h, 1, ts.ctas(), 0, OP_RESIDUAL0), ts, true);
+    PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return !(b.ihist_host[0] < h->precond_tolerance);
+}
+
+// launch nested iterations until the (host-mapped) nested history shows convergence `lag` iterations ago
+template <class EnqueueIteration>
+static void nested_iterations(pps_handle* h, Block& b, EnqueueIteration&& enqueue) {
+    const int lag = std::max(1, h->lag);
+    const int nev = static_cast<int>(h->inner_events.size());
+    int done_at = h->precond_max_iter;
+    for (int it = 0; it < h->precond_max_iter; ++it) {
+        enqueue();
+        PPS_CUDA_CHECK(cudaEventRecord(h->inner_events[it % nev], h->stream));
+        if (it >= lag) {
+            PPS_CUDA_CHECK(cudaEventSynchronize(h->inner_events[(it - lag) % nev]));
+            if (b.ihist_host[it - lag + 1] < h->precond_tolerance) { done_at = it - lag + 1; break; }
+        }
+    }
+    h->precond_iters += done_at;
+}
+
+// ghosts(X) (plain mirrors; BiCGSTAB.hpp:300, baseCG.hpp:237-238 for order 1) and X, B *= norm  (:310-314 / :250-254)
+static void nested_finish(pps_handle* h, Block& b, double* X, double* B, bool reset_x_ghosts, bool check_done) {
+    {
+        // these run although the nested solve is `done` by now; only a converged OUTER solve switches them off
+        InnerScope outer(h, h->ctl);
+        if (reset_x_ghosts) neumann_ghosts(h, b, X, false, check_done);
+    }
+    LaunchScope ls(h, KC_SETUP);
+    inner_scale_kernel<<<148 * 8, 256, 0, h->stream>>>(X, B, b.g.dims.total, b.ictl, check_done ? h->ctl : nullptr, 1);
+    ls.count(1);
+    check_launch("inner_scale");
+}
+
+static void nested_bicgstab(pps_handle* h, Block& b, double* X, double* B, bool check_done) {
+    InnerScope scope(h, b.ictl);
+    const Box box = b.g.solver_box();
+    const Tiling tp = make_tiling(h, b.g, box, false);
+    const Tiling ts = make_tiling(h, b.g, box, true);
+    if (!nested_start(h, b, X, B, b.ir, check_done)) return;
+    copy_field(h, b, b.ip, b.ir);                                                 // BiCGSTAB.hpp:125-126
+    copy_field(h, b, b.ir0, b.ir);
+    const bool parity = h->parity;
+    nested_iterations(h, b, [&]() {
+        // Mp = p (NoneSolver) ; ghosts ; v = A Mp ; r0.v ; alpha                                      :133-164
+        neumann_ghosts(h, b, b.ip, false, true);
+        launch_stencil(h, KC_APPLY_DOT, b, b.ip, box, EpiStoreDot{b.iv, b.ir0}, make_red(h, 1, ts.ctas(), 0, OP_BICG_ALPHA), ts, true);
+        RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
+        if (parity) launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<true>{b.ir, b.iv, 0}, none, tp, true);          // :168-178
+        else        launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<false>{b.ir, b.iv, 0}, none, tp, true);
+        // z = r (NoneSolver) ; ghosts ; t = A z ; r.t, t.t ; omega                                    :181-225
+        neumann_ghosts(h, b, b.ir, false, true);
+        launch_stencil(h, KC_APPLY_DOT2, b, b.ir, box, EpiStoreDot2Self{b.it}, make_red(h, 2, ts.ctas(), 0, OP_BICG_OMEGA), ts, true);
+        RedCtx rho = make_red(h, 2, tp.ctas(), 0, OP_BICG_RHO);                                         // :227-259
+        if (parity) launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdate<true>{X, b.ir, b.ip, b.ir, b.it, b.ir0, 0, 0}, rho, tp, true);
+        else        launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdate<false>{X, b.ir, b.ip, b.ir, b.it, b.ir0, 0, 0}, rho, tp, true);
+        if (parity) launch_pointwise(h, KC_P_UPDATE, b, box, OpPUpdate<true>{b.ip, b.ir, b.iv, 0, 0}, none, tp, true);   // :262-272
+        else        launch_pointwise(h, KC_P_UPDATE, b, box, OpPUpdate<false>{b.ip, b.ir, b.iv, 0, 0}, none, tp, true);
+    });
+    nested_finish(h, b, X, B, true, check_done);
+}
+
+static void chebyshev_local(pps_handle* h, Block& b, double* X, double* B, bool check_done);
+
+static void nested_cg_chebyshev(pps_handle* h, Block& b, double* X, double* B, bool check_done) {
+    InnerScope scope(h, b.ictl);
+    const Box box = b.g.solver_box();
+    const Tiling tp = make_tiling(h, b.g, box, false);
+    const Tiling ts = make_tiling(h, b.g, box, true);
+    if (!nested_start(h, b, X, B, b.ir, check_done)) return;
+    chebyshev_local(h, b, b.iz, b.ir, true);                                      // baseCG.hpp:109
+    copy_field(h, b, b.ip, b.iz);                                                 // :111
+    const bool parity = h->parity;
+    const bool order1 = h->cfg.order_neumann == 1;
+    nested_iterations(h, b, [&]() {
+        if (order1) neumann_ghosts(h, b, b.ip, false, true);                      // :123-124
+        launch_stencil(h, KC_CG_APPLY, b, b.ip, box, EpiCgApply{b.iv, b.ir, b.iz}, make_red(h, 2, ts.ctas(), 0, OP_CG_ALPHA), ts, true);   // :126-151
+        RedCtx none2 = make_red(h, 2, tp.ctas(), 0, OP_NONE);
+        if (parity) launch_pointwise(h, KC_CG_XR, b, box, OpCgXR<true>{X, b.ir, b.ip, b.iv, 0}, none2, tp, true);        // :154-165
+        else        launch_pointwise(h, KC_CG_XR, b, box, OpCgXR<false>{X, b.ir, b.ip, b.iv, 0}, none2, tp, true);
+        chebyshev_local(h, b, b.iz, b.ir, true);                                  // :168
+        launch_pointwise(h, KC_DOT, b, box, OpDot{b.ir, b.iz}, make_red(h, 2, tp.ctas(), 0, OP_CG_BETA), tp, true);      // :171-195
+        RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
+        if (parity) launch_pointwise(h, KC_CG_P, b, box, OpCgP<true>{b.ip, b.iz, 0}, none, tp, true);                   // :197-208
+        else        launch_pointwise(h, KC_CG_P, b, box, OpCgP<false>{b.ip, b.iz, 0}, none, tp, true);
+    });
+    nested_finish(h, b, X, B, order1, check_done);
+}
+
+// X = M(B) for one block: the preconditioner slot of the main solvers
+static void precondition(pps_handle* h, Block& b, double* X, double* B, bool check_done) {
+    switch (h->cfg.precond) {
+        case PPS_PRECOND_NONE: return;
+        case PPS_PRECOND_CHEBYSHEV: chebyshev_local(h, b, X, B, check_done); return;
+        case PPS_PRECOND_BICGSTAB_LOCAL: nested_bicgstab(h, b, X, B, check_done); return;
+        case PPS_PRECOND_CG_CHEB_LOCAL: nested_cg_chebyshev(h, b, X, B, check_done); return;
+        default: throw std::runtime_error("unknown preconditioner");
     }
 }
 
@@ -811,6 +977,7 @@ static void denormalize(pps_handle* h) {
 static void begin_solve(pps_handle* h) {
     h->launch_count = 0;
     h->iter_in_solve = 0;
+    h->precond_iters = 0;
     for (auto& s : h->stats) { s.ms = 0; s.launches = 0; }
     h->event_next = 0;
     Ctl& c = h->ctl_host;
@@ -1071,11 +1238,12 @@ static void bicgstab_iteration_fused(pps_handle* h) {
 
 static void cg_iteration(pps_handle* h) {
     const bool parity = h->parity;
-    // halo(p) (no ghost reset for order 2, baseCG.hpp:123-124); Ap = A p; sum r.z, p.Ap; alpha     :118-151
+    // halo(p); ghost reset only for orderNeumanBcs == 1 (baseCG.hpp:123-124); Ap = A p; sum r.z, p.Ap; alpha     :118-151
+    const bool ghosts = h->cfg.order_neumann == 1;
     if (h->blocks[0].z == h->blocks[0].r)
-        fused_operator(h, KC_CG_APPLY, sel_p, false, 2, OP_CG_ALPHA, [](Block& b) { return EpiCgApplySelf{b.v, b.r}; });
+        fused_operator(h, KC_CG_APPLY, sel_p, ghosts, 2, OP_CG_ALPHA, [](Block& b) { return EpiCgApplySelf{b.v, b.r}; });
     else
-        fused_operator(h, KC_CG_APPLY, sel_p, false, 2, OP_CG_ALPHA, [](Block& b) { return EpiCgApply{b.v, b.r, b.z}; });
+        fused_operator(h, KC_CG_APPLY, sel_p, ghosts, 2, OP_CG_ALPHA, [](Block& b) { return EpiCgApply{b.v, b.r, b.z}; });
     const bool none = h->cfg.precond == PPS_PRECOND_NONE;
     {
         const unsigned int total = total_ctas(h, false);
@@ -1112,11 +1280,75 @@ static void cg_iteration(pps_handle* h) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Chebyshev iteration as the MAIN solver (chebyshevIteration.hpp:48-140 with isMainLoop = true, communicationON = true):
+// chebyshevMax sweeps on the BC-adjusted copy of b, a face exchange + ghost reset before every sweep, no normalisation
+// (normFieldB_ stays 1), x written on the solver range only, then ||b - A x||.  As in precondition(), the two iterates the
+// reference computes and discards are skipped and X = -W is folded into the last live sweep (bit-identical x).
+// ------------------------------------------------------------------------------------------------
+template <bool PAR>
+static void chebyshev_main_sweeps(pps_handle* h) {
+    const int m = h->cfg.cheb_max_iter;
+    const int last = m - 2;   // X = -y_last; validate() guarantees last >= 1
+    const double theta = h->theta, inv_theta = 1.0 / h->theta;
+    double rho_old = 1 / h->sigma;
+    double rho = 1 / (2 * h->sigma - rho_old);
+    const double c1 = 2 * rho / h->delta;
+    // halo(B~); ghosts(B~); Z = B~/theta; Y = c1 (2 B~ + A B~ / theta)                       :69-91
+    fused_operator(h, KC_CHEB_FIRST, sel_t, true, 0, OP_NONE, [=](Block& b) {
+        return EpiChebFirst<PAR>{b.cz, last == 1 ? b.x : b.cy, theta, inv_theta, c1, last == 1 ? -1.0 : 1.0};
+    });
+    for (int c = 2; c <= last; c++) {                                                        // :94-116
+        rho_old = rho;
+        rho = 1 / (2 * h->sigma - rho_old);
+        const bool fin = c == last;
+        const double r1 = rho, r0 = rho_old, s2 = 2 * h->sigma, d2 = 2 / h->delta;
+        fused_operator(h, KC_CHEB_STEP, sel_cy, true, 0, OP_NONE, [=](Block& b) {
+            return EpiChebStep<PAR>{fin ? b.x : b.cw, b.t, b.cz, r1, r0, s2, d2, fin ? -1.0 : 1.0};
+        });
+        for (auto& b : h->blocks) {   // swap(Z, Y); swap(W, Y)  (:114-115)
+            double* tmp = b.cz; b.cz = b.cy; b.cy = tmp;
+            tmp = b.cw; b.cw = b.cy; b.cy = tmp;
+        }
+    }
+}
+
+static void solve_chebyshev_main(pps_handle* h) {
+    begin_solve(h);
+    for (auto& b : h->blocks) { copy_field(h, b, b.t, b.b); adjust_b(h, b, b.t); }          // :61-67
+    PPS_CUDA_CHECK(cudaEventRecord(h->ev_loop0, h->stream));
+    if (h->parity) chebyshev_main_sweeps<true>(h);
+    else           chebyshev_main_sweeps<false>(h);
+    PPS_CUDA_CHECK(cudaEventRecord(h->ev_loop1, h->stream));
+    residual(h, OP_RESIDUAL_FINAL);                                                         // :134-135, with the caller's b
+    download_ctl(h);
+    h->iters = h->cfg.cheb_max_iter;                                                        // :137
+    h->err_op = h->ctl_host.sums[4];
+    h->err_iter = h->err_op;                                                                // :136
+    h->norm_b = 1;
+    h->hist_host[0][0] = h->err_op;
+}
+
 static void solve(pps_handle* h) {
     if (h->operator_only) throw std::runtime_error("this handle was created with PPS_FLAG_OPERATOR_ONLY: no solver vectors");
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
     const auto wall0 = std::chrono::high_resolution_clock::now();
     PPS_CUDA_CHECK(cudaEventRecord(h->ev_start, h->stream));
+    if (h->cfg.solver == PPS_SOLVER_CHEBYSHEV) {
+        solve_chebyshev_main(h);
+        PPS_CUDA_CHECK(cudaEventRecord(h->ev_end, h->stream));
+        PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (h->halo_stream) PPS_CUDA_CHECK(cudaStreamSynchronize(h->halo_stream));
+        if (h->bnd_stream) PPS_CUDA_CHECK(cudaStreamSynchronize(h->bnd_stream));
+        float cms = 0;
+        PPS_CUDA_CHECK(cudaEventElapsedTime(&cms, h->ev_loop0, h->ev_loop1));
+        h->loop_seconds = cms * 1e-3;
+        PPS_CUDA_CHECK(cudaEventElapsedTime(&cms, h->ev_start, h->ev_end));
+        h->solver_seconds = cms * 1e-3;
+        (void)wall0;
+        if (h->profiling) collect_stats(h);
+        return;
+    }
     begin_solve(h);
     const bool cg = h->cfg.solver == PPS_SOLVER_CG;
     // halo(x); ghosts(x) with normFieldB_ = 1; normalise; r = b - A x      BiCGSTAB.hpp:86-112 / baseCG.hpp:69-103
@@ -1147,7 +1379,7 @@ static void solve(pps_handle* h) {
     if (cg) run_iterations(h, [&]() { cg_iteration(h); });
     else if (h->fuse_full) run_iterations(h, [&]() { bicgstab_iteration_fused(h); });
     else    run_iterations(h, [&]() { bicgstab_iteration(h); });
-    end_solve(h, /*reset_x_ghosts=*/!cg);
+    end_solve(h, /*reset_x_ghosts=*/!cg || h->cfg.order_neumann == 1);   // BiCGSTAB.hpp:300 always; baseCG.hpp:237-238 for order 1
     PPS_CUDA_CHECK(cudaEventRecord(h->ev_end, h->stream));
     PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     if (h->halo_stream) PPS_CUDA_CHECK(cudaStreamSynchronize(h->halo_stream));   // exchanges of iterations launched past convergence
@@ -1186,10 +1418,14 @@ static void validate(const pps_config& c, int rank, int world) {
         throw std::runtime_error("configuration of ranks not coherent: world_size " + std::to_string(world) + " ranks " +
                                  std::to_string(c.nranks[0]) + " " + std::to_string(c.nranks[1]) + " " + std::to_string(c.nranks[2]));
     if (rank < 0 || rank >= world) throw std::runtime_error("rank out of range");
-    if (c.order_neumann != 2) throw std::runtime_error("only orderNeumanBcs = 2 is implemented");
-    if (c.solver != PPS_SOLVER_BICGSTAB && c.solver != PPS_SOLVER_CG) throw std::runtime_error("unknown solver");
-    if (c.precond != PPS_PRECOND_NONE && c.precond != PPS_PRECOND_CHEBYSHEV) throw std::runtime_error("unknown preconditioner");
-    if (c.precond == PPS_PRECOND_CHEBYSHEV && c.cheb_max_iter < 3) throw std::runtime_error("chebyshevMax must be >= 3");
+    if (c.order_neumann != 1 && c.order_neumann != 2) throw std::runtime_error("orderNeumanBcs must be 1 or 2");
+    if (c.solver != PPS_SOLVER_BICGSTAB && c.solver != PPS_SOLVER_CG && c.solver != PPS_SOLVER_CHEBYSHEV) throw std::runtime_error("unknown solver");
+    if (c.precond < PPS_PRECOND_NONE || c.precond > PPS_PRECOND_CG_CHEB_LOCAL) throw std::runtime_error("unknown preconditioner");
+    if (c.precond_max_iter < 0 || c.precond_tolerance < 0) throw std::runtime_error("precond_max_iter / precond_tolerance must be >= 0");
+    if (c.solver == PPS_SOLVER_CHEBYSHEV && c.precond != PPS_PRECOND_NONE)
+        throw std::runtime_error("Chebyshev as main solver takes no preconditioner (its T_Preconditioner slot is unused, chebyshevIteration.hpp:143)");
+    if ((c.precond == PPS_PRECOND_CHEBYSHEV || c.precond == PPS_PRECOND_CG_CHEB_LOCAL || c.solver == PPS_SOLVER_CHEBYSHEV) && c.cheb_max_iter < 3)
+        throw std::runtime_error("chebyshevMax must be >= 3");
     if (c.max_iter < 0) throw std::runtime_error("max_iter must be >= 0");
 }
 
@@ -1226,14 +1462,18 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     const int nr = cfg.nranks[0] * cfg.nranks[1] * cfg.nranks[2];
     if (world == 1) for (int r = 0; r < nr; r++) { Block b; b.g = make_block(cfg, r); h->blocks.push_back(std::move(b)); }
     else { Block b; b.g = make_block(cfg, rank); h->blocks.push_back(std::move(b)); }
-    const bool cheb = cfg.precond == PPS_PRECOND_CHEBYSHEV;
+    const bool has_precond = cfg.precond != PPS_PRECOND_NONE;   // any preconditioner: Mp and z are vectors of their own
+    const bool cheb_vectors = cfg.precond == PPS_PRECOND_CHEBYSHEV || cfg.precond == PPS_PRECOND_CG_CHEB_LOCAL;
+    const bool nested = cfg.precond == PPS_PRECOND_BICGSTAB_LOCAL || cfg.precond == PPS_PRECOND_CG_CHEB_LOCAL;
+    if (cfg.precond_max_iter > 0) h->precond_max_iter = cfg.precond_max_iter;
+    if (cfg.precond_tolerance > 0) h->precond_tolerance = cfg.precond_tolerance;
     {
         // 17-pass schedule: opt-in (PPS_FUSE_FULL or PPS_FUSE=2), and only where every halo value of the fused operand can be
         // recomputed locally: one block, no Neumann face, no preconditioner, BiCGSTAB, TMA operator kernels
         const int want = env_int("PPS_FUSE", cfg.fusion);
         bool neumann = false;
         for (int f = 0; f < 6; f++) neumann = neumann || cfg.bcs_type[f] == 1;
-        h->fuse_full = want == PPS_FUSE_FULL && world == 1 && nr == 1 && !neumann && !cheb && cfg.solver == PPS_SOLVER_BICGSTAB &&
+        h->fuse_full = want == PPS_FUSE_FULL && world == 1 && nr == 1 && !neumann && !has_precond && cfg.solver == PPS_SOLVER_BICGSTAB &&
                        h->stencil_impl == 1 && h->by_tma == 8;
         h->fuse_p = env_int("PPS_FUSE_P", 1) != 0;
         h->fuse_s = env_int("PPS_FUSE_S", 1) != 0;
@@ -1252,14 +1492,30 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         b.x = dalloc(b, n, h->stream); b.b = dalloc(b, n, h->stream); b.r = dalloc(b, n, h->stream);
         b.r0 = dalloc(b, n, h->stream); b.p = dalloc(b, n, h->stream); b.v = dalloc(b, n, h->stream);
         b.t = dalloc(b, n, h->stream);
-        if (cheb) {
+        if (has_precond) {
             b.mp = dalloc(b, n, h->stream); b.z = dalloc(b, n, h->stream);
-            b.cy = dalloc(b, n, h->stream); b.cz = dalloc(b, n, h->stream); b.cw = dalloc(b, n, h->stream);
+            if (cheb_vectors) { b.cy = dalloc(b, n, h->stream); b.cz = dalloc(b, n, h->stream); b.cw = dalloc(b, n, h->stream); }
+            if (nested) {
+                b.ip = dalloc(b, n, h->stream); b.ir = dalloc(b, n, h->stream); b.iv = dalloc(b, n, h->stream);
+                if (cfg.precond == PPS_PRECOND_BICGSTAB_LOCAL) { b.ir0 = dalloc(b, n, h->stream); b.it = dalloc(b, n, h->stream); }
+                else b.iz = dalloc(b, n, h->stream);
+                // control block + host-mapped histories of the nested solver
+                const size_t hl = static_cast<size_t>(h->precond_max_iter) + 2;
+                PPS_CUDA_CHECK(cudaHostAlloc(&b.ihist_host, sizeof(double) * 4 * hl, cudaHostAllocMapped));
+                double* hd = nullptr;
+                PPS_CUDA_CHECK(cudaHostGetDevicePointer(&hd, b.ihist_host, 0));
+                Ctl ic{};
+                ic.norm_b = 1;
+                ic.hist_err = hd; ic.hist_alpha = hd + hl; ic.hist_omega = hd + 2 * hl; ic.hist_rho = hd + 3 * hl;
+                PPS_CUDA_CHECK(cudaMalloc(&b.ictl, sizeof(Ctl)));
+                PPS_CUDA_CHECK(cudaMemcpy(b.ictl, &ic, sizeof(Ctl), cudaMemcpyHostToDevice));
+            }
         } else {
             b.mp = b.p;
             b.z = b.r;
         }
-        if (cfg.solver == PPS_SOLVER_CG && !cheb) b.z = b.r;
+        if (cfg.solver == PPS_SOLVER_CG && !has_precond) b.z = b.r;
+        if (cfg.solver == PPS_SOLVER_CHEBYSHEV) { b.cy = dalloc(b, n, h->stream); b.cz = dalloc(b, n, h->stream); b.cw = dalloc(b, n, h->stream); }
         if (h->fuse_full) { b.p2 = dalloc(b, n, h->stream); b.v2 = dalloc(b, n, h->stream); b.s = dalloc(b, n, h->stream); }
         if (world > 1) {
             for (int f = 0; f < 4; f++) {
@@ -1278,6 +1534,7 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     PPS_CUDA_CHECK(cudaMalloc(&h->counter, sizeof(unsigned int)));
     PPS_CUDA_CHECK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), h->stream));
     PPS_CUDA_CHECK(cudaMalloc(&h->ctl, sizeof(Ctl)));
+    h->actl = h->ctl;
     h->hist_len = cfg.max_iter + 2;
     for (int q = 0; q < 4; q++) {
         PPS_CUDA_CHECK(cudaHostAlloc(&h->hist_host[q], sizeof(double) * h->hist_len, cudaHostAllocMapped));
@@ -1290,6 +1547,10 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     h->sigma = h->theta / h->delta;
     h->iter_events.resize(std::max(8, h->lag + 2));
     for (auto& ev : h->iter_events) PPS_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (nested) {
+        h->inner_events.resize(std::max(8, h->lag + 2));
+        for (auto& ev : h->inner_events) PPS_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
     PPS_CUDA_CHECK(cudaEventCreate(&h->ev_start));
     PPS_CUDA_CHECK(cudaEventCreate(&h->ev_loop0));
     PPS_CUDA_CHECK(cudaEventCreate(&h->ev_loop1));
@@ -1341,8 +1602,12 @@ static void destroy(pps_handle* h) {
     if (h->recv_epoch) cudaFree(h->recv_epoch);
     if (h->ar_mail) cudaFree(h->ar_mail);
     if (h->ar_peer_table) cudaFree(h->ar_peer_table);
-    for (auto& b : h->blocks)
+    for (auto& b : h->blocks) {
         for (double* p : b.owned) cudaFree(p);
+        if (b.ictl) cudaFree(b.ictl);
+        if (b.ihist_host) cudaFreeHost(b.ihist_host);
+    }
+    for (auto e : h->inner_events) cudaEventDestroy(e);
     cudaFree(h->partials);
     cudaFree(h->counter);
     cudaFree(h->ctl);
@@ -1544,6 +1809,7 @@ int pps_get_rhs(pps_handle* h, int rank, double* b_host) {
 }
 
 int pps_get_iterations(const pps_handle* h) { return h->iters; }
+long long pps_get_preconditioner_iterations(const pps_handle* h) { return h->precond_iters; }
 double pps_get_error_iteration(const pps_handle* h) { return h->err_iter; }
 double pps_get_error_operator(const pps_handle* h) { return h->err_op; }
 double pps_get_norm_b(const pps_handle* h) { return h->norm_b; }
@@ -1553,7 +1819,8 @@ double pps_get_loop_seconds(const pps_handle* h) { return h->loop_seconds; }
 int pps_get_history(const pps_handle* h, int which, double* out, int capacity) {
     PPS_API_BEGIN
     if (which < 0 || which > 3) throw std::runtime_error("history selector out of range");
-    const int n = which == 0 ? h->iters + 1 : h->iters;
+    // Chebyshev as main solver keeps no history (chebyshevIteration.hpp:132-139): entry 0 is the final residual
+    const int n = h->cfg.solver == PPS_SOLVER_CHEBYSHEV ? (which == 0 ? 1 : 0) : (which == 0 ? h->iters + 1 : h->iters);
     if (capacity < n) throw std::runtime_error("history buffer too small: need " + std::to_string(n));
     std::memcpy(out, h->hist_host[which], sizeof(double) * n);
     PPS_API_END

@@ -59,10 +59,13 @@ def pps_config_from_oracle(ocfg: po.OrcConfig, **over):
     import parallelpoissonsolver_b200 as pps
     kw = dict(
         npglobal=list(ocfg.np), nranks=list(ocfg.nranks), ds=list(ocfg.ds), origin=list(ocfg.origin), bcs=list(ocfg.bcs),
-        solver=pps.SOLVER_CG if ocfg.solver == po.SOLVER_CG else pps.SOLVER_BICGSTAB,
-        precond=pps.PRECOND_CHEBYSHEV if ocfg.precond == po.PRECOND_CHEBYSHEV else pps.PRECOND_NONE,
+        solver={po.SOLVER_CG: pps.SOLVER_CG, po.SOLVER_CHEBYSHEV: pps.SOLVER_CHEBYSHEV}.get(ocfg.solver, pps.SOLVER_BICGSTAB),
+        precond={po.PRECOND_CHEBYSHEV: pps.PRECOND_CHEBYSHEV, po.PRECOND_BICGSTAB_LOCAL: pps.PRECOND_BICGSTAB_LOCAL,
+                 po.PRECOND_CG_CHEB_LOCAL: pps.PRECOND_CG_CHEB_LOCAL}.get(ocfg.precond, pps.PRECOND_NONE),
         tolerance=ocfg.tolerance, max_iter=ocfg.max_iter, cheb_max_iter=ocfg.cheb_max, cheb_epsilon=ocfg.cheb_epsilon,
-        cheb_rescale_min=ocfg.cheb_rescale_min, cheb_rescale_max=ocfg.cheb_rescale_max)
+        cheb_rescale_min=ocfg.cheb_rescale_min, cheb_rescale_max=ocfg.cheb_rescale_max,
+        order_neumann=ocfg.order_neumann if ocfg.order_neumann in (1, 2) else 2,
+        precond_tolerance=ocfg.precond_tolerance, precond_max_iter=ocfg.precond_max_iter)
     kw.update(over)
     return pps.make_config(**kw)
 
