@@ -51,10 +51,10 @@ MIXED = (0, 1, 0, 1, 0, 1)  # shipped default
 
 
 def cfg(np, bcs=DIRICHLET, solver="bicgstab_none", ds=(0.1, 0.1, 0.1), origin=(0, 0, 0), toll_scaling=1e-10,
-        toll_main=100, iter_max=1700, cheb_max=11, order_neumann=2, rescale_min=None, rescale_max=None):
+        toll_main=100, iter_max=1700, cheb_max=11, order_neumann=2, rescale_min=None, rescale_max=None, dim=3):
     return dict(np=tuple(np), bcs=tuple(bcs), solver=solver, ds=tuple(ds), origin=tuple(origin),
                 toll_scaling=toll_scaling, toll_main=toll_main, iter_max=iter_max, cheb_max=cheb_max,
-                order_neumann=order_neumann, rescale_min=rescale_min, rescale_max=rescale_max)
+                order_neumann=order_neumann, rescale_min=rescale_min, rescale_max=rescale_max, dim=dim)
 
 
 # name -> configuration.  "default" is the reference exactly as shipped.
@@ -83,6 +83,13 @@ CONFIGS = {
     "chm24": cfg((24, 20, 28), MIXED, "cheb_main", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), cheb_max=60,
                  rescale_min=1.0, rescale_max=1.0),
     "chd32": cfg((32, 32, 32), DIRICHLET, "cheb_main", cheb_max=25),
+    # DIM = 2 and DIM = 1 (inputParam.hpp:16; argv is then `px py` / `px`, main.cpp:40-48)
+    "q24": cfg((24, 20, 1), MIXED, "bicgstab_none", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), dim=2),
+    "q24_cheb": cfg((24, 20, 1), MIXED, "bicgstab_cheb", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), dim=2),
+    "qd40": cfg((40, 36, 1), DIRICHLET, "bicgstab_none", dim=2),
+    "qcg40": cfg((40, 36, 1), DIRICHLET, "cg_cheb", dim=2),
+    "l48": cfg((48, 1, 1), MIXED, "bicgstab_none", ds=(0.05, 0.1, 0.1), origin=(0.3, -0.2, 0.1), dim=1),
+    "l48_cheb": cfg((48, 1, 1), (1, 0, 0, 0, 0, 0), "bicgstab_cheb", ds=(0.05, 0.1, 0.1), origin=(0.3, -0.2, 0.1), dim=1),
     "d128": cfg((128, 128, 128)),
     # CPU-baseline samples for bench.py --impl reference (bounded: fixed iteration count)
     "bench256": cfg((256, 256, 256), iter_max=10000),
@@ -114,6 +121,7 @@ def make_cfg_dir(name, c):
     p = os.path.join(dst, "inputParam.hpp")
     t = open(p).read()
     t = _sub(t, r"^using T_Solver = .*;$", "using T_Solver = " + SOLVER_TYPEDEFS[c["solver"]] + ";", p)
+    t = _sub(t, r"^constexpr int DIM=\d;", "constexpr int DIM=%d;" % c.get("dim", 3), p)
     t = _sub(t, r"npglobal=\{[^}]*\}", "npglobal={%s}" % ",".join(map(str, c["np"])), p)
     t = _sub(t, r"> ds=\{[^}]*\}", "> ds={%s}" % ",".join(_fmt(float(v)) for v in c["ds"]), p)
     t = _sub(t, r"origin=\{[^}]*\}", "origin={%s}" % ",".join(_fmt(float(v)) for v in c["origin"]), p)

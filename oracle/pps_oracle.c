@@ -62,13 +62,14 @@ void orc_default_config(orc_config* c) {
     c->precond_tolerance = 1e4 * 1e-10;
     c->precond_max_iter = 150;
     c->order_neumann = 2;
+    c->dim = 3;
 }
 
 /* ---------------------------------------------------------------- geometry (blockGrid.hpp) */
-static void eigen_pair(const double ds[3], const int n[3], double out[2]) {
+static void eigen_pair(int dim, const double ds[3], const int n[3], double out[2]) {
     /* blockGrid.hpp:301-340 */
     double emin = 0, emax = 0;
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < dim; i++) {
         double lo = 4 * sin(1 * ORC_PI / 2 / (n[i] + 1)) * sin(1 * ORC_PI / 2 / (n[i] + 1)) / (ds[i] * ds[i]);
         double hi = 4 * sin(n[i] * ORC_PI / 2 / (n[i] + 1)) * sin(n[i] * ORC_PI / 2 / (n[i] + 1)) / (ds[i] * ds[i]);
         emin += lo;
@@ -96,6 +97,13 @@ static void block_init(const orc_config* c, int rank, Block* B) {
         B->hc[2 * d + 1] = many && !last;
         B->ls[2 * d] = B->ld[2 * d] + ((c->bcs[2 * d] == 0 && B->hb[2 * d]) ? 1 : 0);             /* :208-222 */
         B->ls[2 * d + 1] = B->ld[2 * d + 1] - ((c->bcs[2 * d + 1] == 0 && B->hb[2 * d + 1]) ? 1 : 0);
+        if (d >= c->dim) {                                             /* :166-167,178-179,193-204,237,261: one point, no guards, no faces */
+            B->n[d] = 1; B->ng[d] = 1;
+            B->ld[2 * d] = 0; B->ld[2 * d + 1] = 1;
+            B->ls[2 * d] = 0; B->ls[2 * d + 1] = 1;
+            B->hb[2 * d] = B->hb[2 * d + 1] = 0;
+            B->hc[2 * d] = B->hc[2 * d + 1] = 0;
+        }
     }
     B->sj = B->ng[0];
     B->sk = (long)B->ng[0] * B->ng[1];
@@ -105,8 +113,8 @@ static void block_init(const orc_config* c, int rank, Block* B) {
         nl[d] = B->ls[2 * d + 1] - B->ls[2 * d];
         ngl[d] = c->np[d] - (c->bcs[2 * d] == 0) - (c->bcs[2 * d + 1] == 0);
     }
-    eigen_pair(c->ds, nl, B->eig_local);
-    eigen_pair(c->ds, ngl, B->eig_global);
+    eigen_pair(c->dim, c->ds, nl, B->eig_local);
+    eigen_pair(c->dim, c->ds, ngl, B->eig_global);
 }
 
 static double* zalloc(long n) { return (double*)calloc((size_t)n, sizeof(double)); }
@@ -115,11 +123,13 @@ orc_t* orc_create(const orc_config* c) {
     orc_t* o = (orc_t*)calloc(1, sizeof(orc_t));
     o->c = *c;
     if (o->c.order_neumann != 1) o->c.order_neumann = 2;
+    if (o->c.dim != 1 && o->c.dim != 2) o->c.dim = 3;
+    for (int d = o->c.dim; d < 3; d++) o->c.nranks[d] = 1;                  /* main.cpp:40-48 */
     o->world = c->nranks[0] * c->nranks[1] * c->nranks[2];
     o->blk = (Block*)calloc((size_t)o->world, sizeof(Block));
     for (int r = 0; r < o->world; r++) {
         Block* B = &o->blk[r];
-        block_init(c, r, B);
+        block_init(&o->c, r, B);
         B->x = zalloc(B->ntot); B->b = zalloc(B->ntot);
         B->p = zalloc(B->ntot); B->r = zalloc(B->ntot); B->r0 = zalloc(B->ntot);
         B->Mp = zalloc(B->ntot); B->AMp = zalloc(B->ntot); B->z = zalloc(B->ntot); B->Az = zalloc(B->ntot);
@@ -230,6 +240,11 @@ long orc_neumann_face(const orc_t* o, int rank, int face, double* out) {
 static inline double stencil(const orc_t* o, const Block* B, const double* d, int i, int j, int k) {
     const double* ds = o->c.ds;
     const long sj = B->sj, sk = B->sk;
+    if (o->c.dim == 1)                                                            /* :24-27 */
+        return (d[i - 1] - 2 * d[i] + d[i + 1]) / (ds[0] * ds[0]);
+    if (o->c.dim == 2)                                                            /* :28-32 */
+        return (d[i - 1 + sj * j] - 2 * d[i + sj * j] + d[i + 1 + sj * j]) / (ds[0] * ds[0])
+             + (d[i + sj * (j - 1)] - 2 * d[i + sj * j] + d[i + sj * (j + 1)]) / (ds[1] * ds[1]);
     return (d[i - 1 + sj * j + sk * k] - 2 * d[i + sj * j + sk * k] + d[i + 1 + sj * j + sk * k]) / (ds[0] * ds[0])
          + (d[i + sj * (j - 1) + sk * k] - 2 * d[i + sj * j + sk * k] + d[i + sj * (j + 1) + sk * k]) / (ds[1] * ds[1])
          + (d[i + sj * j + sk * (k - 1)] - 2 * d[i + sj * j + sk * k] + d[i + sj * j + sk * (k + 1)]) / (ds[2] * ds[2]);

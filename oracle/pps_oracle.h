@@ -44,6 +44,7 @@ typedef struct orc_config {
     double precond_tolerance; /* tollPreconditionerSolver * tollScalingFactor   solverSetup.hpp:31 (nested Krylov preconditioners) */
     int precond_max_iter;     /* iterMaxPreconditioner   solverSetup.hpp:32 */
     int order_neumann;        /* orderNeumanBcs: 2 (shipped) or 1   solverSetup.hpp:25 */
+    int dim;                  /* DIM: 3 (shipped), 2 or 1   inputParam.hpp:16; axes >= dim hold one point, no guards (blockGrid.hpp:160-206) */
 } orc_config;
 
 typedef struct orc_block_info {

@@ -54,6 +54,13 @@ CASES = [
     # Chebyshev iteration as main solver (fixed number of sweeps, no history)
     ("chm24", (1, 1, 1), True), ("chm24", (1, 1, 2), True), ("chm24", (3, 2, 1), False),
     ("chd32", (1, 1, 1), True), ("chd32", (2, 2, 2), False),
+    # DIM = 2 and DIM = 1
+    ("q24", (1, 1, 1), True), ("q24", (2, 1, 1), False), ("q24", (3, 2, 1), True),
+    ("q24_cheb", (1, 1, 1), True), ("q24_cheb", (2, 2, 1), False),
+    ("qd40", (1, 1, 1), True), ("qd40", (2, 3, 1), False),
+    ("qcg40", (1, 1, 1), True), ("qcg40", (2, 2, 1), False),
+    ("l48", (1, 1, 1), True), ("l48", (4, 1, 1), True),
+    ("l48_cheb", (1, 1, 1), True), ("l48_cheb", (2, 1, 1), False),
 ]
 
 
@@ -80,7 +87,9 @@ def assemble(outdir, world, npglobal):
         ng, nn, loc = m["nlocal_guards"], m["nlocal_noguards"], m["global_location"]
         x = np.fromfile(f"{outdir}/rank{r}.x").reshape(ng[2], ng[1], ng[0])
         o = [loc[d] * nn[d] for d in range(3)]
-        g[o[2]:o[2] + nn[2], o[1]:o[1] + nn[1], o[0]:o[0] + nn[0]] = x[1:-1, 1:-1, 1:-1]
+        # axes >= DIM hold one point without guards (blockGrid.hpp:160-182)
+        inner = tuple(slice(1, -1) if ng[d] > nn[d] else slice(None) for d in (2, 1, 0))
+        g[o[2]:o[2] + nn[2], o[1]:o[1] + nn[1], o[0]:o[0] + nn[0]] = x[inner]
     return g
 
 
@@ -104,7 +113,7 @@ def run_case(name, ranks, store_x):
             origin=np.array(c["origin"], dtype=float), bcs=np.array(c["bcs"]),
             solver=c["solver"].split("_")[0], precond=c["solver"].split("_")[1], cheb_max=c["cheb_max"],
             max_point_error=float(maxerr[0].split()[4]) if maxerr else np.nan,
-            order_neumann=c.get("order_neumann", 2),
+            order_neumann=c.get("order_neumann", 2), dim=c.get("dim", 3),
             cheb_rescale_min=500.0 if c.get("rescale_min") is None else float(c["rescale_min"]),
             cheb_rescale_max=1 - 1e-4 if c.get("rescale_max") is None else float(c["rescale_max"]),
         )

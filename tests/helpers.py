@@ -27,6 +27,8 @@ def oracle_config_from_golden(g, nranks=None, max_iter=None, tolerance=None):
     if "order_neumann" in g:   # fixtures written before these knobs existed are order 2 with the shipped rescaling
         extra = dict(order_neumann=int(g["order_neumann"]), cheb_rescale_min=float(g["cheb_rescale_min"]),
                      cheb_rescale_max=float(g["cheb_rescale_max"]))
+    if "dim" in g:
+        extra["dim"] = int(g["dim"])
     precond = {"cheb": po.PRECOND_CHEBYSHEV, "bicgloc": po.PRECOND_BICGSTAB_LOCAL, "cgcheb": po.PRECOND_CG_CHEB_LOCAL}.get(str(g["precond"]), po.PRECOND_NONE)
     return po.make_config(
         np_=[int(v) for v in g["np"]], nranks=[int(v) for v in (g["nranks"] if nranks is None else nranks)],
@@ -42,7 +44,9 @@ def assemble_global(fields, blocks, npglobal):
         nn = [bi[0][d] for d in range(3)]
         loc = [bi[1][d] for d in range(3)]
         o = [loc[d] * nn[d] for d in range(3)]
-        out[o[2]:o[2] + nn[2], o[1]:o[1] + nn[1], o[0]:o[0] + nn[0]] = f[1:-1, 1:-1, 1:-1]
+        # axes >= DIM hold one point without guards (blockGrid.hpp:160-182)
+        inner = tuple(slice(1, -1) if f.shape[a] > nn[d] else slice(None) for a, d in ((0, 2), (1, 1), (2, 0)))
+        out[o[2]:o[2] + nn[2], o[1]:o[1] + nn[1], o[0]:o[0] + nn[0]] = f[inner]
     return out
 
 
