@@ -15,11 +15,19 @@ class BlockGrid {
               const std::array<int, 6>& bcsType, const std::array<T_data, 6>& bcsValue)
         : nranks_(nranks), rank_(my_rank), npglobal_(npglobal), ds_(ds), origin_(origin), guards_(guards), bcsType_(bcsType),
           bcsValue_(bcsValue) {
-        static_assert(DIM == 3, "the B200 path implements DIM = 3");
+        static_assert(DIM >= 1 && DIM <= 3, "DIM must be 1, 2 or 3");
         location_ = {my_rank % nranks[0], (my_rank / nranks[0]) % nranks[1], my_rank / (nranks[0] * nranks[1])};
         ntotGuards_ = ntotNoGuards_ = 1;
         numComm_ = 0;
         for (int d = 0; d < 3; d++) {
+            if (d >= DIM) {
+                // an unused axis holds one point, no guards, no faces (blockGrid.hpp:166-167,178-179,193-204)
+                nlocal_[d] = nlocalGuards_[d] = 1;
+                limitsData_[2 * d] = limitsSolver_[2 * d] = 0;
+                limitsData_[2 * d + 1] = limitsSolver_[2 * d + 1] = 1;
+                hasBoundary_[2 * d] = hasBoundary_[2 * d + 1] = hasComm_[2 * d] = hasComm_[2 * d + 1] = false;
+                continue;
+            }
             nlocal_[d] = npglobal[d] / nranks[d];
             nlocalGuards_[d] = nlocal_[d] + 2 * guards[d];
             ntotGuards_ *= nlocalGuards_[d];
@@ -36,11 +44,12 @@ class BlockGrid {
             limitsSolver_[2 * d + 1] = limitsData_[2 * d + 1] - ((bcsType[2 * d + 1] == 0 && last) ? 1 : 0);
         }
         limitsComm_ = limitsData_;
-        for (int d = 0; d < 3; d++) {
+        numElementsComm_ = {0, 0, 0};
+        for (int d = 0; d < DIM; d++) {
             if (hasComm_[2 * d + 1]) limitsComm_[2 * d] = limitsData_[2 * d + 1] - guards[d];
             if (hasComm_[2 * d]) limitsComm_[2 * d + 1] = limitsData_[2 * d] + guards[d];
             numElementsComm_[d] = 1;
-            for (int e = 0; e < 3; e++)
+            for (int e = 0; e < DIM; e++)
                 if (e != d) numElementsComm_[d] *= nlocal_[e];
         }
         eigen(true);
@@ -70,12 +79,16 @@ class BlockGrid {
     bool checkBCsSet() const { return false; }
     const std::array<T_data, 2> getEigenValuesLocal() const { return eigLocal_; }
     const std::array<T_data, 2> getEigenValuesGlobal() const { return eigGlobal_; }
-    int getNtotNpglobal() const { return npglobal_[0] * npglobal_[1] * npglobal_[2]; }
+    int getNtotNpglobal() const {
+        int n = 1;
+        for (int d = 0; d < DIM; d++) n *= npglobal_[d];
+        return n;
+    }
 
   private:
     void eigen(bool global) {
         T_data lo = 0, hi = 0;
-        for (int d = 0; d < 3; d++) {
+        for (int d = 0; d < DIM; d++) {
             const int n = global ? npglobal_[d] - (bcsType_[2 * d] == 0) - (bcsType_[2 * d + 1] == 0)
                                  : limitsSolver_[2 * d + 1] - limitsSolver_[2 * d];
             const T_data a = std::sin(1 * PI / 2 / (n + 1)), b = std::sin(n * PI / 2 / (n + 1));

@@ -111,10 +111,10 @@ def default_config() -> Config:
 def make_config(npglobal, nranks=(1, 1, 1), ds=(0.1, 0.1, 0.1), origin=(0.0, 0.0, 0.0), bcs=(0, 0, 0, 0, 0, 0),
                 solver=SOLVER_BICGSTAB, precond=PRECOND_NONE, tolerance=1e-8, max_iter=1700, cheb_max_iter=11,
                 cheb_epsilon=1e-4, cheb_rescale_min=500.0, cheb_rescale_max=1 - 1e-4, arithmetic=ARITH_FAST,
-                fusion=FUSE_AUTO, device=-1, flags=0, order_neumann=2, precond_tolerance=1e4 * 1e-10, precond_max_iter=150) -> Config:
+                fusion=FUSE_AUTO, device=-1, flags=0, order_neumann=2, precond_tolerance=1e4 * 1e-10, precond_max_iter=150, dim=3) -> Config:
     c = Config()
     c.abi_version = ABI_VERSION
-    c.dim = 3
+    c.dim = int(dim)
     c.npglobal[:] = list(npglobal)
     c.nranks[:] = list(nranks)
     c.ds[:] = [float(v) for v in ds]

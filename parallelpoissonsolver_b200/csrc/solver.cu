@@ -1403,11 +1403,16 @@ static void solve(pps_handle* h) {
 // ------------------------------------------------------------------------------------------------
 static void validate(const pps_config& c, int rank, int world) {
     if (c.abi_version != PPS_ABI_VERSION) throw std::runtime_error("pps_config.abi_version mismatch");
-    if (c.dim != 3) throw std::runtime_error("only DIM = 3 is implemented");
+    if (c.dim < 1 || c.dim > 3) throw std::runtime_error("DIM must be 1, 2 or 3");
     const int nr = c.nranks[0] * c.nranks[1] * c.nranks[2];
     for (int d = 0; d < 3; d++) {
         if (c.nranks[d] < 1 || c.npglobal[d] < 1) throw std::runtime_error("bad npglobal / nranks");
-        if (c.guards[d] != 1) throw std::runtime_error("guards must be 1 (7-point stencil)");
+        if (d >= c.dim) {
+            // main.cpp:40-48 reads only DIM rank counts; the unused axes hold one point (blockGrid.hpp:166-167)
+            if (c.nranks[d] != 1) throw std::runtime_error("nranks must be 1 along the axes >= DIM");
+            continue;
+        }
+        if (c.guards[d] != 1) throw std::runtime_error("guards must be 1 (second-order centred stencil)");
         if (c.npglobal[d] / c.nranks[d] < 3) throw std::runtime_error("blocks need at least 3 points per axis");
         if (!(c.ds[d] > 0)) throw std::runtime_error("ds must be positive");
     }
@@ -1458,6 +1463,12 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         h->coef.ds[d] = cfg.ds[d];
         h->coef.ds2[d] = cfg.ds[d] * cfg.ds[d];
         h->coef.inv[d] = 1.0 / (cfg.ds[d] * cfg.ds[d]);
+        if (d >= cfg.dim) {
+            // DIM < 3 (matrixFreeOperatorA.hpp:24-32): no term along this axis.  Its guard planes are zero, so the 3-D kernels
+            // add (0 - 2u + 0) / inf = -0 (PARITY) or (..) * 0 (FAST)
+            h->coef.ds2[d] = std::numeric_limits<double>::infinity();
+            h->coef.inv[d] = 0.0;
+        }
     }
     const int nr = cfg.nranks[0] * cfg.nranks[1] * cfg.nranks[2];
     if (world == 1) for (int r = 0; r < nr; r++) { Block b; b.g = make_block(cfg, r); h->blocks.push_back(std::move(b)); }
@@ -1473,7 +1484,7 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         const int want = env_int("PPS_FUSE", cfg.fusion);
         bool neumann = false;
         for (int f = 0; f < 6; f++) neumann = neumann || cfg.bcs_type[f] == 1;
-        h->fuse_full = want == PPS_FUSE_FULL && world == 1 && nr == 1 && !neumann && !has_precond && cfg.solver == PPS_SOLVER_BICGSTAB &&
+        h->fuse_full = want == PPS_FUSE_FULL && world == 1 && nr == 1 && cfg.dim == 3 && !neumann && !has_precond && cfg.solver == PPS_SOLVER_BICGSTAB &&
                        h->stencil_impl == 1 && h->by_tma == 8;
         h->fuse_p = env_int("PPS_FUSE_P", 1) != 0;
         h->fuse_s = env_int("PPS_FUSE_S", 1) != 0;
@@ -1620,15 +1631,20 @@ static void destroy(pps_handle* h) {
 }
 
 // host (reference layout) <-> device (pitched layout)
+// (DIM < 3: the host array has no guards along the unused axes, blockGrid.hpp:172-182; on the device it is row j = 1 /
+//  plane k = 1 of the 3-D layout, whose other rows / planes stay zero)
+static long long host_origin(const Block& b) {
+    return kOff + (b.g.dim < 2 ? b.g.dims.pitch : 0) + (b.g.dim < 3 ? b.g.dims.plane : 0);
+}
 static void upload_field(pps_handle* h, const Block& b, double* dev, const double* host) {
     const size_t w = sizeof(double) * (b.g.n[0] + 2);
-    PPS_CUDA_CHECK(cudaMemcpy2DAsync(dev + kOff, sizeof(double) * b.g.dims.pitch, host, w, w,
-                                     static_cast<size_t>(b.g.n[1] + 2) * (b.g.n[2] + 2), cudaMemcpyHostToDevice, h->stream));
+    PPS_CUDA_CHECK(cudaMemcpy2DAsync(dev + host_origin(b), sizeof(double) * b.g.dims.pitch, host, w, w,
+                                     static_cast<size_t>(b.g.ref_extent(1)) * b.g.ref_extent(2), cudaMemcpyHostToDevice, h->stream));
 }
 static void download_field(pps_handle* h, const Block& b, double* host, const double* dev) {
     const size_t w = sizeof(double) * (b.g.n[0] + 2);
-    PPS_CUDA_CHECK(cudaMemcpy2DAsync(host, w, dev + kOff, sizeof(double) * b.g.dims.pitch, w,
-                                     static_cast<size_t>(b.g.n[1] + 2) * (b.g.n[2] + 2), cudaMemcpyDeviceToHost, h->stream));
+    PPS_CUDA_CHECK(cudaMemcpy2DAsync(host, w, dev + host_origin(b), sizeof(double) * b.g.dims.pitch, w,
+                                     static_cast<size_t>(b.g.ref_extent(1)) * b.g.ref_extent(2), cudaMemcpyDeviceToHost, h->stream));
 }
 
 }  // namespace pps
@@ -1710,11 +1726,13 @@ int pps_block_info_get(const pps_handle* h, int rank, pps_block_info* out) {
     for (int d = 0; d < 3; d++) {
         out->global_location[d] = g.loc[d];
         out->nlocal_noguards[d] = g.n[d];
-        out->nlocal_guards[d] = g.n[d] + 2;
+        out->nlocal_guards[d] = g.ref_extent(d);
     }
     for (int f = 0; f < 6; f++) {
-        out->limits_data[f] = g.ld[f];
-        out->limits_solver[f] = g.ls[f];
+        // reference numbering: an unused axis (>= DIM) has no guards, its single point is index 0 (blockGrid.hpp:193-204)
+        const int shift = (f / 2 >= g.dim) ? 1 : 0;
+        out->limits_data[f] = g.ld[f] - shift;
+        out->limits_solver[f] = g.ls[f] - shift;
         out->has_boundary[f] = g.hb[f];
         out->has_communication[f] = g.hc[f];
     }
@@ -1745,7 +1763,7 @@ int pps_set_neumann_face(pps_handle* h, int rank, int face, const double* dudn_h
     PPS_API_BEGIN
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
     Block* b = find_block(h, rank);
-    if (face < 0 || face > 5) throw std::runtime_error("face out of range");
+    if (face < 0 || face >= 2 * b->g.dim) throw std::runtime_error("face out of range");
     int u, v;
     b->g.tangential(face, u, v);
     const size_t want = static_cast<size_t>(b->g.n[u]) * b->g.n[v];
@@ -1835,10 +1853,11 @@ int pps_check_solution(pps_handle* h, int rank, const double* u_exact_host, doub
     download_field(h, *b, x.data(), b->x);
     PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     // checkSolutionLocalGlobal (iterativeSolverBase.hpp:300-317): data range, reporting only
-    const long long sj = b->g.n[0] + 2, sk = sj * (b->g.n[1] + 2);
+    const long long sj = b->g.ref_extent(0), sk = sj * b->g.ref_extent(1);
+    const int j0 = b->g.dim >= 2 ? 1 : 0, k0 = b->g.dim >= 3 ? 1 : 0;   // unused axes: the single point is index 0
     double s = 0, m = -1;
-    for (int k = 1; k <= b->g.n[2]; k++)
-        for (int j = 1; j <= b->g.n[1]; j++)
+    for (int k = k0; k < k0 + b->g.n[2]; k++)
+        for (int j = j0; j < j0 + b->g.n[1]; j++)
             for (int i = 1; i <= b->g.n[0]; i++) {
                 const double e = std::abs(x[i + sj * j + sk * k] - u_exact_host[i + sj * j + sk * k]);
                 s += e;

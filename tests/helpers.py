@@ -69,7 +69,8 @@ def pps_config_from_oracle(ocfg: po.OrcConfig, **over):
         tolerance=ocfg.tolerance, max_iter=ocfg.max_iter, cheb_max_iter=ocfg.cheb_max, cheb_epsilon=ocfg.cheb_epsilon,
         cheb_rescale_min=ocfg.cheb_rescale_min, cheb_rescale_max=ocfg.cheb_rescale_max,
         order_neumann=ocfg.order_neumann if ocfg.order_neumann in (1, 2) else 2,
-        precond_tolerance=ocfg.precond_tolerance, precond_max_iter=ocfg.precond_max_iter)
+        precond_tolerance=ocfg.precond_tolerance, precond_max_iter=ocfg.precond_max_iter,
+        dim=ocfg.dim if ocfg.dim in (1, 2) else 3)
     kw.update(over)
     return pps.make_config(**kw)
 

@@ -1,6 +1,6 @@
 """GPU parity tests of the SURVEY.md section 8(f) items that were written after the round-1 GPU budget was spent:
 first-order Neumann closure (orderNeumanBcs = 1), Chebyshev iteration as MAIN solver, nested Krylov preconditioners
-(local BiCGSTAB, local CG + Chebyshev).  The oracle side of each is pinned bit for bit to the unmodified reference on the
+(local BiCGSTAB, local CG + Chebyshev), DIM = 2 and DIM = 1.  The oracle side of each is pinned bit for bit to the unmodified reference on the
 CPU (tests/test_oracle.py); the CUDA side has not run on a GPU yet, so these tests are opt-in until it has:
 
     PPS_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_next.py -m gpu -x -q
@@ -125,6 +125,53 @@ def test_nested_preconditioner_against_reference_golden(name):
         assert np.max(np.abs(hs[:n] - hg[:n]) / hg[:n]) <= 1e-2
     assert s.error_operator < 1.5 * float(g["tolerance"])
     assert s.preconditioner_iterations > 0
+    if "x" in g:
+        assert H.rel_l2(H.pps_global_solution(s, o.cfg), g["x"]) <= 2e-6
+    s.close(); o.close()
+
+
+# ---------------------------------------------------------------- DIM = 2 and DIM = 1
+LOWDIM = [(2, (24, 20, 1), (0, 1, 0, 1, 0, 0)), (2, (67, 9, 1), (1, 0, 1, 0, 0, 0)), (2, (130, 7, 1), (0, 0, 0, 0, 0, 0)),
+          (1, (48, 1, 1), (0, 1, 0, 0, 0, 0)), (1, (131, 1, 1), (1, 0, 0, 0, 0, 0))]
+
+
+@pytest.mark.parametrize("dim,shape,bcs", LOWDIM)
+def test_low_dimensional_operator_parity_bit_exact(dim, shape, bcs):
+    """matrixFreeOperatorA.hpp:24-32: the 3-D kernels run with zero guard planes and an infinite spacing along the unused axes,
+    which adds (0 - 2u + 0) / inf = -0 per unused axis: the same bits as the reference's 1-D / 2-D formulas"""
+    pps = _pps()
+    ocfg = po.make_config(shape, bcs=bcs, dim=dim, ds=(0.1, 0.12, 0.09))
+    o = po.Oracle(ocfg)
+    s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, arithmetic=pps.ARITH_PARITY))
+    assert s.shape(0) == o.shape(0)
+    bi, bo = s.block(0), o.block(0)
+    assert list(bi.limits_solver) == list(bo.limits_solver) and list(bi.nlocal_guards) == list(bo.nguards)
+    rng = np.random.default_rng(3)
+    u = rng.standard_normal(o.shape(0))
+    want = o.apply(0, u)
+    got = s.apply_operator(0, u)
+    ls = bo.limits_solver
+    box = (slice(ls[4], ls[5]), slice(ls[2], ls[3]), slice(ls[0], ls[1]))
+    assert np.array_equal(got[box], want[box])
+    sf = pps.PoissonSolver(H.pps_config_from_oracle(ocfg))
+    gf = sf.apply_operator(0, u)
+    scale = np.abs(u).max() * 2 * sum(1 / ocfg.ds[d] ** 2 for d in range(dim))
+    assert np.max(np.abs(gf[box] - want[box])) <= 8 * np.finfo(float).eps * scale
+    s.close(); sf.close(); o.close()
+
+
+@pytest.mark.parametrize("name", ["q24_111", "q24_211", "q24_321", "q24_cheb_111", "q24_cheb_221", "qd40_111", "qd40_231",
+                                  "qcg40_111", "qcg40_221", "l48_111", "l48_411", "l48_cheb_111", "l48_cheb_211"])
+def test_low_dimensional_solves_against_reference_golden(name):
+    g, o, s = _from_golden(name)
+    s.solve()
+    hs, hg = s.history(), g["history"]
+    assert abs(s.norm_b - float(g["norm_b"])) <= 1e-13 * float(g["norm_b"])
+    n10 = min(11, len(hs), len(hg))
+    assert np.max(np.abs(hs[:n10] - hg[:n10]) / hg[:n10]) <= 1e-10
+    it = int(g["iters"])
+    assert 0.9 * it - 2 <= s.iterations <= 1.06 * it + 2, (s.iterations, it)
+    assert s.error_operator < 1.5 * float(g["tolerance"])
     if "x" in g:
         assert H.rel_l2(H.pps_global_solution(s, o.cfg), g["x"]) <= 2e-6
     s.close(); o.close()
