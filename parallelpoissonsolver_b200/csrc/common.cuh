@@ -55,6 +55,10 @@ struct HaloWait {
     unsigned int epoch;
     int lo_plane, hi_plane;     // guard planes that are being received (-1: none)
     int shift;                  // rotation of blockIdx.z
+    // peer-memory transport (PPS_OVERLAP=3): one flag per face, written by the NEIGHBOUR's copy engine -> system scope.
+    // Trailing members, so the existing five-value initialisers leave them null / 0.
+    const unsigned int* flag_hi;   // flag of the upper face (nullptr: `flag` covers both faces)
+    int sys_scope;                 // 1: acquire at system scope
 };
 
 struct Coef {

@@ -743,11 +743,7 @@ __global__ void face_copy_kernel(double* __restrict__ dst, const double* __restr
     }
 }
 
-// peer-memory halo path: publish / await the epoch of an exchange through a flag in (peer) device memory
-__global__ void publish_epoch_sys_kernel(unsigned int* flag, unsigned int epoch) {
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
-}
+// peer-memory halo path: await the epoch a neighbour's copy engine writes into my flag after its plane has landed
 __global__ void await_epoch_sys_kernel(const unsigned int* flag, unsigned int epoch) {
     unsigned int v;
     do {

@@ -132,7 +132,8 @@ struct pps_handle {
     cudaStream_t launch_stream = nullptr;   // stream the operator launchers use right now (stream or bnd_stream)
     cudaEvent_t ev_pre = nullptr, ev_bnd_done = nullptr;
     cudaEvent_t ev_field_ready = nullptr, ev_halo_done = nullptr;
-    int overlap = 1;                  // 0 serial; 1 interior first, boundary chunks after the exchange; 2 in-kernel wait (experimental)
+    int overlap = 1;                  // 0 serial; 1 interior first, boundary chunks after the exchange; 2 in-kernel wait over NCCL
+                                      // (experimental, can deadlock); 3 in-kernel wait over the SM-free peer transport (experimental)
     unsigned int* halo_flag = nullptr;   // device: epoch of the last exchange that has landed
     unsigned int halo_epoch = 0;
     HaloWait wait_next{nullptr, 0, -1, -1, 0};   // consumed by the next TMA operator launch
@@ -144,6 +145,8 @@ struct pps_handle {
     unsigned int* peer_flags[2] = {nullptr, nullptr};                      // neighbour's recv_epoch array
     unsigned int* recv_epoch = nullptr;                                    // mine: [field][face lo/hi], written by the neighbours
     unsigned int field_epoch[2] = {0, 0};
+    unsigned int* epoch_ring = nullptr;   // pinned host: source words of the flag DMAs (the host runs a few exchanges ahead)
+    unsigned int epoch_ring_next = 0;
     std::vector<void*> ipc_opened;
     // peer-memory allreduce fused into the reducing kernels (PPS_ALLREDUCE_P2P=1)
     bool ar_p2p = false;
@@ -527,6 +530,8 @@ static void halo_exchange(pps_handle* h, FieldSel sel, bool check_done, bool on_
 // exchanges of the same field are always separated by the scalar allreduces of the iteration, which every rank
 // only passes after its operator launches that read the previous content have completed.
 // ------------------------------------------------------------------------------------------------
+constexpr unsigned int kEpochRing = 4096;   // flag DMAs in flight are bounded by the host's run-ahead (PPS_LAG iterations)
+
 struct PeerInfo {
     long long pid;
     int device;
@@ -542,6 +547,7 @@ static void setup_p2p(pps_handle* h) {
     if (!(b.g.hc[4] || b.g.hc[5]) || h->cfg.solver != PPS_SOLVER_BICGSTAB) return;
     PPS_CUDA_CHECK(cudaMalloc(&h->recv_epoch, 4 * sizeof(unsigned int)));
     PPS_CUDA_CHECK(cudaMemsetAsync(h->recv_epoch, 0, 4 * sizeof(unsigned int), h->stream));
+    PPS_CUDA_CHECK(cudaHostAlloc(&h->epoch_ring, kEpochRing * sizeof(unsigned int), cudaHostAllocDefault));
     PeerInfo mine{};
     mine.pid = static_cast<long long>(getpid());
     mine.device = h->device;
@@ -639,9 +645,13 @@ static unsigned int halo_push_p2p(pps_handle* h, int fidx, double* fld) {
         const long long kguard = up ? 0 : b.g.n[2] + 1;            // the neighbour's guard plane that faces me
         PPS_CUDA_CHECK(cudaMemcpyAsync(h->peer_field[up][fidx] + kguard * b.g.dims.plane, fld + kdata * b.g.dims.plane,
                                        sizeof(double) * static_cast<size_t>(b.g.dims.plane), cudaMemcpyDefault, h->halo_stream));
-        // my upper neighbour receives on ITS lower face (slot 0), my lower neighbour on its upper face (slot 1)
-        publish_epoch_sys_kernel<<<1, 1, 0, h->halo_stream>>>(h->peer_flags[up] + 2 * fidx + (up ? 0 : 1), epoch);
-        ls.count(1);
+        // my upper neighbour receives on ITS lower face (slot 0), my lower neighbour on its upper face (slot 1).  The flag is a
+        // second DMA (4 bytes from a pinned host word) ordered after the plane by the stream: no SM takes part in the
+        // transport, so receivers may wait inside a running kernel (PPS_OVERLAP=3) without starving the sender.
+        unsigned int* word = h->epoch_ring + (h->epoch_ring_next++ % kEpochRing);
+        *word = epoch;
+        PPS_CUDA_CHECK(cudaMemcpyAsync(h->peer_flags[up] + 2 * fidx + (up ? 0 : 1), word, sizeof(unsigned int), cudaMemcpyDefault,
+                                       h->halo_stream));
     }
     check_launch("halo_push_p2p");
     return epoch;
@@ -1088,7 +1098,17 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
         const bool z_only = !(b.g.hc[0] || b.g.hc[1] || b.g.hc[2] || b.g.hc[3]);
         if (ghosts) neumann_ghosts(h, b, sel(b), false, true);
         const Tiling t_all = make_tiling(h, b.g, b.g.solver_box(), true);
-        if (!use_p2p && z_only && h->stencil_impl == 1 && h->overlap == 2 && t_all.grid.z >= 3) {
+        if (use_p2p && h->stencil_impl == 1 && h->overlap == 3 && t_all.grid.z >= 3) {
+            // EXPERIMENTAL (PPS_OVERLAP=3, needs PPS_HALO_P2P=1): ONE launch; the TMA producers of the first / last z-chunk wait
+            // in-kernel for the neighbours' epoch flags.  Unlike PPS_OVERLAP=2 the transport is pure DMA (halo_push_p2p), so the
+            // waiting CTAs cannot keep a communication kernel off the SMs.
+            const Box box = b.g.solver_box();
+            const Tiling t = t_all;
+            h->wait_next = HaloWait{h->recv_epoch + 2 * p2p_field, p2p_epoch, b.g.hc[4] ? 0 : -1, b.g.hc[5] ? b.g.n[2] + 1 : -1,
+                                    (b.g.hc[4] && t.grid.z > 1) ? 1 : 0, h->recv_epoch + 2 * p2p_field + 1, 1};
+            RedCtx red = make_red(h, nacc, t.ctas(), 0, op);
+            launch_stencil(h, kc, b, sel(b), box, make_epi(b), red, t, true);
+        } else if (!use_p2p && z_only && h->stencil_impl == 1 && h->overlap == 2 && t_all.grid.z >= 3) {
             // EXPERIMENTAL (PPS_OVERLAP=2): ONE launch; the first / last z-chunk run last and their TMA producer waits in-kernel
             // for the faces.  Fastest when it works, but it needs the NCCL kernel to become resident while waiting CTAs hold
             // the SMs -- CUDA gives no such forward-progress guarantee (it deadlocked on 8 GPUs), hence not the default.
@@ -1611,6 +1631,7 @@ static void destroy(pps_handle* h) {
     if (h->halo_flag) cudaFree(h->halo_flag);
     for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
     if (h->recv_epoch) cudaFree(h->recv_epoch);
+    if (h->epoch_ring) cudaFreeHost(h->epoch_ring);
     if (h->ar_mail) cudaFree(h->ar_mail);
     if (h->ar_peer_table) cudaFree(h->ar_peer_table);
     for (auto& b : h->blocks) {

@@ -59,10 +59,11 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
 
 // spin until the halo stream has published `epoch` (monotonic counter), then order the following bulk-tensor read
 // (async proxy) after the acquire
-__device__ __forceinline__ void wait_halo_flag(const unsigned int* flag, unsigned int epoch) {
+__device__ __forceinline__ void wait_halo_flag(const unsigned int* flag, unsigned int epoch, int sys_scope = 0) {
     unsigned int v;
     do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (sys_scope) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        else           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (static_cast<int>(v - epoch) >= 0) break;
         __nanosleep(200);
     } while (true);
@@ -131,7 +132,8 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid
                     // aux streams are only read where the operator is evaluated: planes kb .. ke-1
                     const bool with_aux = NAUX > 0 && p >= 1 && p <= nplanes - 2;
                     const int kk = kb - 1 + p;
-                    if (hw.flag != nullptr && (kk == hw.lo_plane || kk == hw.hi_plane)) wait_halo_flag(hw.flag, hw.epoch);
+                    if (hw.flag != nullptr && (kk == hw.lo_plane || kk == hw.hi_plane))
+                        wait_halo_flag((kk == hw.hi_plane && hw.flag_hi != nullptr) ? hw.flag_hi : hw.flag, hw.epoch, hw.sys_scope);
                     mbar_arrive_expect_tx(&full[s], with_aux ? SM::kStageBytes : SM::kMainBytes);
                     tma_load_3d(dst, &tmap, &full[s], col0 - kTmaLead, y0 - 1, kk);
                     if (with_aux) {

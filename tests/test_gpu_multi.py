@@ -65,11 +65,12 @@ EXPERIMENTAL = os.environ.get("PPS_TEST_EXPERIMENTAL") == "1"
 
 @pytest.mark.skipif(not EXPERIMENTAL, reason="experimental paths: set PPS_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("env", [{"PPS_HALO_P2P": "1"}, {"PPS_ALLREDUCE_P2P": "1"}, {"PPS_HALO_P2P": "1", "PPS_ALLREDUCE_P2P": "1"},
-                                 {"PPS_OVERLAP": "0"}, {"PPS_OVERLAP": "2"}])
+                                 {"PPS_OVERLAP": "0"}, {"PPS_OVERLAP": "2"}, {"PPS_HALO_P2P": "1", "PPS_OVERLAP": "3"},
+                                 {"PPS_HALO_P2P": "1", "PPS_OVERLAP": "3", "PPS_ALLREDUCE_P2P": "1"}])
 @pytest.mark.parametrize("flags", [(), ("cheb",)])
 def test_two_gpus_slab_transport_variants(env, flags):
-    """the same parity check with the peer-memory halo path (CUDA IPC + copy engines), the serial exchange and the
-    in-kernel-wait overlap"""
+    """the same parity check with the peer-memory halo path (CUDA IPC + copy engines), the serial exchange, the
+    in-kernel-wait overlap over NCCL (PPS_OVERLAP=2) and over the SM-free peer transport (PPS_OVERLAP=3)"""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     _run((1, 1, 2), flags, env)

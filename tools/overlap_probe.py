@@ -8,7 +8,8 @@ Three timed variants of the same fixed-length BiCGSTAB loop on 1x1xN z-slabs (SU
   serial    PPS_OVERLAP=0         exchange, then the whole operator, on one stream
   overlap   PPS_OVERLAP=1         exchange on the halo stream while the interior box is computed
 hidden = 1 - (t_overlap - t_no_comm) / (t_serial - t_no_comm), times = device loop time per iteration, max over ranks.
-Optional extra variants: --p2p (PPS_HALO_P2P=1: CUDA-IPC peer pushes on copy engines), --inkernel (PPS_OVERLAP=2).
+Optional extra variants: --p2p (PPS_HALO_P2P=1: CUDA-IPC peer pushes on copy engines, with the 3-stream schedule and with the
+single-launch in-kernel wait PPS_OVERLAP=3), --inkernel (PPS_OVERLAP=2).
 """
 import json
 import os
@@ -41,6 +42,8 @@ def main():
                 ("overlap", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "1", "PPS_HALO_P2P": "0"})]
     if "--p2p" in sys.argv:
         variants.append(("p2p", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "1", "PPS_HALO_P2P": "1"}))
+    if "--p2p" in sys.argv:
+        variants.append(("p2p_inkernel", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "3", "PPS_HALO_P2P": "1"}))
     if "--inkernel" in sys.argv:
         variants.append(("inkernel", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "2", "PPS_HALO_P2P": "0"}))
     for name, env in variants:
