@@ -48,6 +48,7 @@ two)
     step overlap_default 200 $TORCHRUN --nproc-per-node 2 tools/overlap_probe.py 1024 1024 256 150
     step overlap_p2p 200 $TORCHRUN --nproc-per-node 2 tools/overlap_probe.py 1024 1024 256 150 --p2p
     step bench2 400 $TORCHRUN --nproc-per-node 2 bench.py --gpus 2 --steps 2 --warmup 3 --watchdog 350
+    PPS_HALO_P2P=1 PPS_OVERLAP=3 step bench2_p2p_inkernel 400 $TORCHRUN --nproc-per-node 2 bench.py --gpus 2 --steps 2 --warmup 3 --watchdog 350 --no-cpu-baseline
     PPS_HALO_P2P=1 PPS_ALLREDUCE_P2P=1 step bench2_p2p 400 $TORCHRUN --nproc-per-node 2 bench.py --gpus 2 --steps 2 --warmup 3 --watchdog 350 --no-cpu-baseline
     ;;
 eight)
