@@ -69,6 +69,31 @@ def test_archived_run_norm_b():
         o.close()
 
 
+def test_archived_run_first_iterations():
+    """solverPoissonMPI_CPU/run/solverScoreP.o:10-11, the reference's own archived log (shipped default problem, 4x4x4 MPI ranks):
+         Debug in BiCGSTAB iter 10 alpha 2.15438 omega 1.27489 rho0 1.00433e-05 error 0.1177
+         Debug in BiCGSTAB iter 20 alpha 2.36951 omega 1.56154 rho0 2.98229e-09 error 0.0594782
+    The oracle on the same 64-rank layout prints the same six digits (one unit in the last place of rho0 at iteration 20:
+    the archived run summed with a real MPI_Allreduce, whose order differs from the shim's rank order).  Later lines drift apart --
+    BiCGSTAB amplifies such differences -- and both converge (155 iterations archived, 149 here)."""
+    c = po.OrcConfig()
+    po.lib().orc_default_config(c)
+    c.nranks[:] = (4, 4, 4)
+    c.max_iter = 20
+    o = po.Oracle(c)
+    o.set_problem()
+    o.solve()
+    a, w, r = o.scalar_histories()
+    h = o.history()
+    archived = {10: (2.15438, 1.27489, 1.00433e-05, 0.1177), 20: (2.36951, 1.56154, 2.98229e-09, 0.0594782)}
+    for it, want in archived.items():
+        got = (a[it - 1], w[it - 1], r[it - 1], h[it])
+        for g, v in zip(got, want):
+            assert abs(g - v) <= 1.5e-5 * abs(v), (it, got, want)     # 6 significant digits, +/- 1 in the last one
+        assert "%.6g" % got[0] == "%.6g" % want[0] and "%.6g" % got[1] == "%.6g" % want[1] and "%.6g" % got[3] == "%.6g" % want[3]
+    o.close()
+
+
 def test_archived_run_geometry():
     """solverScoreP.o:4-9: 4x4x4 ranks of 128x128x256 -> local 32 32 64, guards 34 34 66, rank 0 limits."""
     c = po.OrcConfig()
