@@ -94,6 +94,25 @@ def test_archived_run_first_iterations():
     o.close()
 
 
+@pytest.mark.slow
+def test_archived_run_converged_error_lines():
+    """solverScoreP.o:25-27: 155 iterations, 'Max error local block avg 0.0155235 in rank 63', 'Max error local point 0.0254452 in
+    rank 63'.  At tolerance 1e-8 the algebraic error is visible in these numbers and the trajectory is chaotic, so the oracle's
+    full run on the same layout (149 iterations, 0.0160078 / 0.0258967, rank 63) agrees to a few per cent, the worst rank exactly."""
+    c = po.OrcConfig()
+    po.lib().orc_default_config(c)
+    c.nranks[:] = (4, 4, 4)
+    o = po.Oracle(c)
+    o.set_problem()
+    o.solve()
+    assert 0.9 * 155 <= o.iters <= 1.06 * 155
+    s, m = o.check_solution()
+    assert int(np.argmax(s)) == 63 and int(np.argmax(m)) == 63
+    assert abs(s[63] / (32 * 32 * 64) - 0.0155235) <= 0.08 * 0.0155235
+    assert abs(m[63] - 0.0254452) <= 0.08 * 0.0254452
+    o.close()
+
+
 def test_archived_run_geometry():
     """solverScoreP.o:4-9: 4x4x4 ranks of 128x128x256 -> local 32 32 64, guards 34 34 66, rank 0 limits."""
     c = po.OrcConfig()
