@@ -139,6 +139,11 @@ struct pps_handle {
     HaloWait wait_next{nullptr, 0, -1, -1, 0};   // consumed by the next TMA operator launch
     int debug_no_halo = 0;            // timing experiments only: skip the exchange (wrong results)
     int batch_ghosts = 0;             // PPS_BATCH_GHOSTS=1: all Neumann faces of a block in one launch (unverified, round 2)
+    // PPS_GRAPH=1 (unverified, round 2): one Krylov iteration is captured into a CUDA graph at its first launch and replayed;
+    // every iteration enqueues the same kernels with the same arguments (the scalars live in `ctl` on the device)
+    bool use_graph = false;
+    cudaGraphExec_t iter_graph = nullptr;
+    long long iter_graph_launches = 0;   // kernels per replay (for pps_get_launch_count)
     // peer-memory halo path (PPS_HALO_P2P=1, z-slabs): neighbours' field / flag arrays mapped through CUDA IPC
     bool p2p = false;
     double* peer_field[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [lo/hi neighbour][0 = Mp, 1 = z]
@@ -1017,8 +1022,33 @@ static void run_iterations(pps_handle* h, EnqueueIteration&& enqueue) {
     const int lag = std::max(1, h->lag);
     const int nev = static_cast<int>(h->iter_events.size());
     const double tol = h->cfg.tolerance;
+    const bool graph = h->use_graph && !h->profiling;
     for (int it = 0; it < h->cfg.max_iter; ++it) {
-        enqueue();
+        if (graph) {
+            if (h->iter_graph == nullptr) {
+                // capture ONE iteration (launch-bound small grids: ~160 dependent launches per preconditioned iteration)
+                const long long before = h->launch_count;
+                cudaGraph_t g = nullptr;
+                PPS_CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+                try {
+                    enqueue();
+                } catch (...) {
+                    cudaStreamEndCapture(h->stream, &g);
+                    if (g) cudaGraphDestroy(g);
+                    throw;
+                }
+                PPS_CUDA_CHECK(cudaStreamEndCapture(h->stream, &g));
+                cudaError_t e = cudaGraphInstantiate(&h->iter_graph, g, 0);
+                cudaGraphDestroy(g);
+                PPS_CUDA_CHECK(e);
+                h->iter_graph_launches = h->launch_count - before;
+                h->launch_count = before;
+            }
+            PPS_CUDA_CHECK(cudaGraphLaunch(h->iter_graph, h->stream));
+            h->launch_count += h->iter_graph_launches;
+        } else {
+            enqueue();
+        }
         PPS_CUDA_CHECK(cudaEventRecord(h->iter_events[it % nev], h->stream));
         if (it >= lag) {
             PPS_CUDA_CHECK(cudaEventSynchronize(h->iter_events[(it - lag) % nev]));
@@ -1477,6 +1507,9 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     h->overlap = env_int("PPS_OVERLAP", 1);
     h->debug_no_halo = env_int("PPS_DEBUG_NO_HALO", 0);
     h->batch_ghosts = env_int("PPS_BATCH_GHOSTS", 0);
+    // graphs: one block-set on one GPU, iteration-invariant launches only (no ping-pong schedule, no host-synchronising nested solves)
+    h->use_graph = env_int("PPS_GRAPH", 0) != 0 && world == 1 && cfg.precond != PPS_PRECOND_BICGSTAB_LOCAL &&
+                   cfg.precond != PPS_PRECOND_CG_CHEB_LOCAL;
     PPS_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->launch_stream = h->stream;
     for (int d = 0; d < 3; d++) {
@@ -1512,6 +1545,7 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     unsigned long long max_ctas = 0;
     h->operator_only = (cfg.flags & PPS_FLAG_OPERATOR_ONLY) != 0;
     if (h->operator_only) h->fuse_full = false;
+    if (h->fuse_full) h->use_graph = false;
     for (auto& b : h->blocks) {
         const long long n = b.g.dims.total;
         if (h->operator_only) {
@@ -1629,6 +1663,7 @@ static void destroy(pps_handle* h) {
     if (h->ev_field_ready) cudaEventDestroy(h->ev_field_ready);
     if (h->ev_halo_done) cudaEventDestroy(h->ev_halo_done);
     if (h->halo_flag) cudaFree(h->halo_flag);
+    if (h->iter_graph) cudaGraphExecDestroy(h->iter_graph);
     for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
     if (h->recv_epoch) cudaFree(h->recv_epoch);
     if (h->epoch_ring) cudaFreeHost(h->epoch_ring);

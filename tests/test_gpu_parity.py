@@ -388,3 +388,28 @@ def test_batched_neumann_ghosts_bitwise(monkeypatch):
         s.close(); o.close()
     assert np.array_equal(res["0"][0], res["1"][0]) and np.array_equal(res["0"][1], res["1"][1])
     assert res["1"][2] < res["0"][2]
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="unverified round-2 paths: set PPS_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("solver,precond", [(po.SOLVER_BICGSTAB, po.PRECOND_CHEBYSHEV), (po.SOLVER_BICGSTAB, po.PRECOND_NONE),
+                                            (po.SOLVER_CG, po.PRECOND_CHEBYSHEV)])
+def test_graph_replay_is_bitwise_identical(monkeypatch, solver, precond):
+    """PPS_GRAPH=1 replays one captured iteration: same kernels, same arguments, same order -> same bits, and a repeat solve
+    re-uses the instantiated graph"""
+    pps = _pps()
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PPS_GRAPH", mode)
+        o, s = _pair((24, 20, 28), nranks=(1, 1, 2), bcs=(0, 1, 0, 1, 0, 1), solver=solver, precond=precond)
+        o.set_problem()
+        H.hand_over_problem(o, s)
+        s.save_fields()
+        s.solve()
+        first = (s.history().copy(), s.get_solution(0).copy(), s.launch_count)
+        s.restore_fields()
+        s.solve()
+        assert np.array_equal(first[0], s.history()) and np.array_equal(first[1], s.get_solution(0))
+        res[mode] = first
+        s.close(); o.close()
+    assert np.array_equal(res["0"][0], res["1"][0]) and np.array_equal(res["0"][1], res["1"][1])
+    assert res["0"][2] == res["1"][2]

@@ -29,7 +29,11 @@ one)
     step gpu_suite 900 python -m pytest tests -m gpu -x -q -k "not multi and not driver"
     # 2. what round 1 wrote without a GPU: orderNeumanBcs = 1, Chebyshev as main solver, nested Krylov, batched ghosts
     PPS_TEST_EXPERIMENTAL=1 step next_paths 600 python -m pytest tests/test_gpu_next.py -m gpu -q
-    PPS_TEST_EXPERIMENTAL=1 step batched_ghosts 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -k batched
+    PPS_TEST_EXPERIMENTAL=1 step batched_ghosts 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "batched or graph"
+    # launch-bound shipped default problem (128x128x256, Chebyshev): stream launches vs graph replay vs graph + batched ghosts
+    step default_stream 120 parallelpoissonsolver_b200/driver/solverPoisson 1 1 1
+    PPS_GRAPH=1 step default_graph 120 parallelpoissonsolver_b200/driver/solverPoisson 1 1 1
+    PPS_GRAPH=1 PPS_BATCH_GHOSTS=1 step default_graph_batched 120 parallelpoissonsolver_b200/driver/solverPoisson 1 1 1
     step drivers 600 python -m pytest tests/test_gpu_driver.py -m gpu -q
     # 3. the 17-pass schedule: reproduce / bisect the 512^3 repeat-solve anomaly
     step fused_fixed 300 python tools/fused_check.py 128 256 512
