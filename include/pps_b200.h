@@ -175,6 +175,16 @@ int pps_set_max_iterations(pps_handle* h, int max_iter);
 /* out[r*n .. r*n+n) = in of rank r, on every rank: the error gather of checkSolutionLocalGlobal
  * (iterativeSolverBase.hpp:320-373, point-to-point to rank 0 in the reference).  world_size == 1: a copy. */
 int pps_allgather(pps_handle* h, const double* in_host, int n, double* out_host);
+/* diagnostics of the 17-pass schedule: `reps` launches of ONE fused operator kernel (which: 0 = s-update + operator,
+ * 1 = p-update + operator) on frozen pseudo-random inputs, outputs compared bit for bit with the split kernels.
+ * variant = ring stages (3, 4, 6; 16 = 6 stages + cross-proxy fence).  out[0] differing operand entries (summed over
+ * reps), out[1] differing A*operand entries, out[2] launches whose sums differ, out[3] launches with any difference,
+ * out[4..7] pitch, plane, z-chunk, CTAs; out[8 + 5 e ..] = (rep, n_operand, first index, n_result, first index) of the
+ * first four bad launches.  Needs a handle created with PPS_FUSE_FULL. */
+int pps_debug_fused(pps_handle* h, int which, int variant, int reps, long long* out, int nout);
+/* diagnostics: n doubles of a device array of block 0 from element `offset` of the pitched layout (0 s, 1 t, 2 p2, 3 v2, 4 r,
+ * 5 v, 6 p, 7 r0, 8 x).  With a negative `reps` pps_debug_fused stops at the first bad launch and leaves the arrays in place. */
+int pps_debug_peek(pps_handle* h, int array, long long offset, int n, double* out);
 int pps_device_count(void);                                   /* CUDA devices visible to this process */
 
 #ifdef __cplusplus

@@ -95,6 +95,9 @@ CONFIGS = {
     "bench256": cfg((256, 256, 256), iter_max=10000),
     "bench512_it8": cfg((512, 512, 512), iter_max=8),
     "bench1024_it2": cfg((1024, 1024, 1024), iter_max=2),
+    # lock-step goldens of the benchmarked configurations (BASELINE.json configs[1], [2]): the first 20 iterations
+    "bench512_it20": cfg((512, 512, 512), iter_max=20),
+    "bench1024_it20": cfg((1024, 1024, 1024), iter_max=20),
 }
 
 CXX = os.environ.get("CXX", "g++")

@@ -16,6 +16,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -87,8 +88,12 @@ int dumpMain(int argc, char** argv) {
         m << "\neig_global " << grid.getEigenValuesGlobal()[0] << " " << grid.getEigenValuesGlobal()[1];
         m << "\neig_local " << grid.getEigenValuesLocal()[0] << " " << grid.getEigenValuesLocal()[1] << "\n";
     }
-    writeRaw(base + ".x0", x.data(), ntot);
-    writeRaw(base + ".b0", b.data(), ntot);
+    // PPS_DUMP_LIGHT=1 (large grids): only the final x is written, not the inputs and not b
+    const bool light = std::getenv("PPS_DUMP_LIGHT") != nullptr;
+    if (!light) {
+        writeRaw(base + ".x0", x.data(), ntot);
+        writeRaw(base + ".b0", b.data(), ntot);
+    }
 
     // norm of the BC-adjusted right-hand side, computed on copies (collective call)
     T_data normB = 1;
@@ -107,7 +112,7 @@ int dumpMain(int argc, char** argv) {
     MPI_Barrier(MPI_COMM_WORLD);
 
     writeRaw(base + ".x", x.data(), ntot);
-    writeRaw(base + ".b", b.data(), ntot);
+    if (!light) writeRaw(base + ".b", b.data(), ntot);
 
     if (rank == 0) {
         const int iters = solver.getNumIterationFinal();

@@ -97,6 +97,8 @@ def load_library():
     L.pps_synchronize.argtypes = [P]
     L.pps_set_max_iterations.argtypes = [P, C.c_int]
     L.pps_allgather.argtypes = [P, D, C.c_int, D]
+    L.pps_debug_fused.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_int]
+    L.pps_debug_peek.argtypes = [P, C.c_int, C.c_longlong, C.c_int, D]
     L.pps_device_count.restype = C.c_int
     _lib = L
     return L
@@ -310,6 +312,17 @@ class PoissonSolver:
     @property
     def launch_count(self) -> int:
         return self.L.pps_get_launch_count(self.h)
+
+    def debug_fused(self, which: int, variant: int, reps: int):
+        """see pps_debug_fused (include/pps_b200.h)"""
+        out = (C.c_longlong * 32)()
+        self._ck(self.L.pps_debug_fused(self.h, which, variant, reps, out, 32))
+        return list(out)
+
+    def debug_peek(self, array: int, offset: int, n: int) -> np.ndarray:
+        out = np.zeros(n)
+        self._ck(self.L.pps_debug_peek(self.h, array, offset, n, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     def synchronize(self):
         self._ck(self.L.pps_synchronize(self.h))

@@ -59,6 +59,7 @@ def build_driver(force: bool = False) -> str:
         return ""
     deps = _sources(DRIVER_DIR, (".cpp", ".hpp", ".h")) + _sources(os.path.join(ROOT, "include"), (".h", ".hpp"))
     if not force and not _newer(exe, deps + [LIB]):
+        build_driver_host()
         return exe
     cxx = os.environ.get("CXX", "g++")
     cmd = [cxx, "-std=c++17", "-O3", "-DNDEBUG", "-pthread", "-I" + os.path.join(ROOT, "include"),
@@ -67,7 +68,27 @@ def build_driver(force: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("driver build failed:\n%s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    build_driver_host(force=True)
     return exe
+
+
+DRIVER_HOST_LIB = os.path.join(DRIVER_DIR, "libpps_driver_host.so")
+
+
+def build_driver_host(force: bool = False) -> str:
+    """libpps_driver_host.so: the driver's host-side setProblem() as a C-callable helper (driver/setproblem.cpp) for
+    callers that are not C++ (bench.py, tools/).  No CUDA, no oracle code."""
+    src = os.path.join(DRIVER_DIR, "setproblem.cpp")
+    deps = [src, os.path.join(DRIVER_DIR, "solverSetup.hpp")]
+    if not force and not _newer(DRIVER_HOST_LIB, deps):
+        return DRIVER_HOST_LIB
+    cxx = os.environ.get("CXX", "g++")
+    cmd = [cxx, "-std=c++17", "-O3", "-DNDEBUG", "-pthread", "-fPIC", "-shared", "-I" + DRIVER_DIR,
+           "-I" + os.path.join(ROOT, "include", "reference_compat"), src, "-o", DRIVER_HOST_LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("driver host helper build failed:\n%s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return DRIVER_HOST_LIB
 
 
 if __name__ == "__main__":

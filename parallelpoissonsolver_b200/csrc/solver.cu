@@ -108,6 +108,8 @@ struct pps_handle {
     bool operator_only = false; // PPS_FLAG_OPERATOR_ONLY: only p, v, r0 exist
     bool fuse_full = false;     // 17-pass schedule (single block, all-Dirichlet, no preconditioner)
     bool fuse_p = true, fuse_s = true;   // PPS_FUSE_P / PPS_FUSE_S: enable the two fused kernels separately (diagnostics)
+    int fuse_check = 0;                  // PPS_FUSE_CHECK=1 (with PPS_FUSE_P=0): verify every fused_s launch against the split kernels
+    int fuse_check_events = 0;
     int iter_in_solve = 0;      // host-side count of enqueued iterations of the running solve
     std::vector<Block> blocks;
     cudaStream_t stream = nullptr;
@@ -373,11 +375,11 @@ static void launch_tma_inst(pps_handle* h, const Block& b, const double* u, cons
     h->wait_next = HaloWait{nullptr, 0, -1, -1, 0};
 }
 
-template <int BY, int STAGES, bool PAR, class Pre, class Epi>
+template <int BY, int STAGES, bool PAR, int DBG = 0, class Pre, class Epi>
 static void launch_tma_pre(pps_handle* h, int kc, const Block& b, const Box& box, const Pre& pre, const Epi& epi, const RedCtx& red,
                            const Tiling& t, bool check_done) {
     LaunchScope ls(h, kc);
-    auto kern = stencil_tma_pre_kernel<BY, STAGES, PAR, Pre, Epi>;
+    auto kern = stencil_tma_pre_kernel<BY, STAGES, PAR, Pre, Epi, DBG>;
     constexpr int smem = TmaPreSmem<BY, STAGES, Pre::NIN, Epi::NAUX>::kBytes;
     if (h->smem_opt_in.insert(reinterpret_cast<const void*>(kern)).second)
         PPS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1236,6 +1238,37 @@ static void bicgstab_iteration(pps_handle* h) {
     }
 }
 
+__global__ void compare_bits_kernel(const double* __restrict__ a, const double* __restrict__ b, long long n, unsigned long long* out);
+
+// PPS_FUSE_CHECK=1 (diagnostics, needs PPS_FUSE_P=0 so that p2 / v2 are free): recompute s and t with the split kernels
+// from the same r, v, alpha and compare bit for bit; host-synchronous, prints the first mismatches to stderr
+static void fused_s_check(pps_handle* h, Block& b, const Box& box, const Tiling& ts, const Tiling& tp) {
+    static unsigned long long* cnt = nullptr;
+    if (!cnt) PPS_CUDA_CHECK(cudaMalloc(&cnt, 4 * sizeof(unsigned long long)));
+    const unsigned long long init[4] = {0, ~0ull, 0, ~0ull};
+    PPS_CUDA_CHECK(cudaMemcpyAsync(cnt, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    copy_field(h, b, b.p2, b.r);
+    RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
+    launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<false>{b.p2, b.v, 0}, none, tp, true);
+    launch_stencil(h, KC_APPLY, b, b.p2, box, EpiStore{b.v2}, none, ts, true);
+    compare_bits_kernel<<<148 * 8, 256, 0, h->stream>>>(b.s, b.p2, b.g.dims.total, cnt);
+    compare_bits_kernel<<<148 * 8, 256, 0, h->stream>>>(b.t, b.v2, b.g.dims.total, cnt + 2);
+    unsigned long long got[4];
+    PPS_CUDA_CHECK(cudaMemcpyAsync(got, cnt, sizeof(got), cudaMemcpyDeviceToHost, h->stream));
+    PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if ((got[0] || got[2]) && h->fuse_check_events++ < 12) {
+        auto dec = [&](unsigned long long i, char* buf) {
+            const long long k = i / b.g.dims.plane, j = (i % b.g.dims.plane) / b.g.dims.pitch, c = i % b.g.dims.pitch;
+            std::snprintf(buf, 64, "(i=%lld j=%lld k=%lld)", c - kOff, j, k);
+        };
+        char a[64] = "-", c[64] = "-";
+        if (got[0]) dec(got[1], a);
+        if (got[2]) dec(got[3], c);
+        std::fprintf(stderr, "[fuse_check] enqueued iteration %d: s differs in %llu cells, first %s; t differs in %llu cells, first %s\n",
+                     h->iter_in_solve, got[0], a, got[2], c);
+    }
+}
+
 // PPS_FUSE_FULL: the same iteration in 3 kernels / 17 vector passes.  p and v are double-buffered (other CTAs still read
 // the previous p and v on their halo while this CTA stores the new ones) and s gets its own array for the same reason.
 static void bicgstab_iteration_fused(pps_handle* h) {
@@ -1267,6 +1300,7 @@ static void bicgstab_iteration_fused(pps_handle* h) {
             if (h->parity) launch_tma_pre<8, 6, true>(h, KC_FUSED_S, b, box, PreSUpdate<true>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, ts, true);
             else           launch_tma_pre<8, 6, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, ts, true);
         }
+        if (h->fuse_check && !h->fuse_p) fused_s_check(h, b, box, ts, tp);
         {   // x += alpha p + omega s ; r = s - omega t ; sum r0.r, r.r ; beta, rho     :227-259
             RedCtx red = make_red(h, 2, tp.ctas(), 0, OP_BICG_RHO);
             if (h->parity) launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdateS<true>{b.x, b.r, b.p, b.s, b.t, b.r0, 0, 0}, red, tp, true);
@@ -1541,6 +1575,7 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
                        h->stencil_impl == 1 && h->by_tma == 8;
         h->fuse_p = env_int("PPS_FUSE_P", 1) != 0;
         h->fuse_s = env_int("PPS_FUSE_S", 1) != 0;
+        h->fuse_check = env_int("PPS_FUSE_CHECK", 0);
     }
     unsigned long long max_ctas = 0;
     h->operator_only = (cfg.flags & PPS_FLAG_OPERATOR_ONLY) != 0;
@@ -1701,6 +1736,126 @@ static void download_field(pps_handle* h, const Block& b, double* host, const do
     const size_t w = sizeof(double) * (b.g.n[0] + 2);
     PPS_CUDA_CHECK(cudaMemcpy2DAsync(host, w, dev + host_origin(b), sizeof(double) * b.g.dims.pitch, w,
                                      static_cast<size_t>(b.g.ref_extent(1)) * b.g.ref_extent(2), cudaMemcpyDeviceToHost, h->stream));
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics of the fused operator kernels (pps_debug_fused): repeat ONE fused launch on frozen inputs and compare
+// its outputs bit for bit with the split kernels' result
+// ------------------------------------------------------------------------------------------------
+struct OpFillHash {
+    static constexpr int NACC = 0;
+    double* out;
+    unsigned long long seed;
+    __device__ __forceinline__ void begin(const Ctl*) {}
+    __device__ __forceinline__ double val(long long i) const {
+        unsigned long long z = static_cast<unsigned long long>(i) * 0x9E3779B97F4A7C15ull + seed;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return static_cast<double>(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+    }
+    __device__ __forceinline__ void operator()(long long idx, bool m0, bool m1, double*) const {
+        st2(out + idx, make_double2(val(idx), val(idx + 1)), m0, m1);
+    }
+};
+
+// out[0] += number of differing entries, out[1] = min index of a differing entry
+__global__ void compare_bits_kernel(const double* __restrict__ a, const double* __restrict__ b, long long n, unsigned long long* out) {
+    unsigned long long cnt = 0, first = ~0ull;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (__double_as_longlong(a[i]) != __double_as_longlong(b[i])) {
+            cnt++;
+            if (static_cast<unsigned long long>(i) < first) first = static_cast<unsigned long long>(i);
+        }
+    if (cnt) {
+        atomicAdd(out, cnt);
+        atomicMin(out + 1, first);
+    }
+}
+
+static void debug_fused(pps_handle* h, int which, int variant, int reps, long long* out, int nout) {
+    if (!h->fuse_full) throw std::runtime_error("pps_debug_fused needs a handle created with PPS_FUSE_FULL");
+    PPS_CUDA_CHECK(cudaSetDevice(h->device));
+    for (int q = 0; q < nout; q++) out[q] = 0;
+    Block& b = h->blocks[0];
+    const Box box = b.g.solver_box();
+    const Tiling ts = make_tiling(h, b.g, box, true);
+    const Tiling tp = make_tiling(h, b.g, box, false);
+    const long long n = b.g.dims.total;
+    RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
+    h->ctl_host.done = 0; h->ctl_host.alpha = 0.37; h->ctl_host.beta = 0.81; h->ctl_host.omega = 0.53;
+    upload_ctl(h);
+    PPS_CUDA_CHECK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), h->stream));
+    launch_pointwise(h, KC_SETUP, b, box, OpFillHash{b.r, 1}, none, tp, false);
+    launch_pointwise(h, KC_SETUP, b, box, OpFillHash{b.v, 2}, none, tp, false);
+    launch_pointwise(h, KC_SETUP, b, box, OpFillHash{b.p, 3}, none, tp, false);
+    launch_pointwise(h, KC_SETUP, b, box, OpFillHash{b.r0, 4}, none, tp, false);
+    // reference with the split kernels: operand into p2, A*operand into v2
+    double *u_ref = b.p2, *au_ref = b.v2, *u_out = b.s, *au_out = b.t;
+    zero_field(h, b, u_ref); zero_field(h, b, au_ref); zero_field(h, b, u_out); zero_field(h, b, au_out);
+    const int nacc = which == 0 ? 2 : 1;
+    if (which == 0) {
+        copy_field(h, b, u_ref, b.r);
+        launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<false>{u_ref, b.v, 0}, none, tp, false);
+        launch_stencil(h, KC_APPLY_DOT2, b, u_ref, box, EpiStoreDot2Self{au_ref}, make_red(h, 2, ts.ctas(), 0, OP_NONE), ts, false);
+    } else {
+        copy_field(h, b, u_ref, b.p);
+        launch_pointwise(h, KC_P_UPDATE, b, box, OpPUpdate<false>{u_ref, b.r, b.v, 0, 0}, none, tp, false);
+        launch_stencil(h, KC_APPLY_DOT, b, u_ref, box, EpiStoreDot{au_ref, b.r0}, make_red(h, 1, ts.ctas(), 0, OP_NONE), ts, false);
+    }
+    download_ctl(h);
+    double sums_ref[2] = {h->ctl_host.sums[0], h->ctl_host.sums[1]};
+    unsigned long long* cnt = nullptr;
+    PPS_CUDA_CHECK(cudaMalloc(&cnt, 4 * sizeof(unsigned long long)));
+    int events = 0;
+    const bool stop_on_bad = reps < 0;   // negative count: stop at the first bad launch and leave every array as it is (pps_debug_peek)
+    if (reps < 0) reps = -reps;
+    for (int rep = 0; rep < reps; rep++) {
+        const unsigned long long init[4] = {0, ~0ull, 0, ~0ull};
+        PPS_CUDA_CHECK(cudaMemcpyAsync(cnt, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+        RedCtx red = make_red(h, nacc, ts.ctas(), 0, OP_NONE);
+        if (which == 0) {
+            const PreSUpdate<false> pre{u_out, b.r, b.v, 0};
+            const EpiStoreDot2Self epi{au_out};
+            switch (variant) {
+                case 3: launch_tma_pre<8, 3, false>(h, KC_FUSED_S, b, box, pre, epi, red, ts, true); break;
+                case 4: launch_tma_pre<8, 4, false>(h, KC_FUSED_S, b, box, pre, epi, red, ts, true); break;
+                case 6: launch_tma_pre<8, 6, false>(h, KC_FUSED_S, b, box, pre, epi, red, ts, true); break;
+                case 16: launch_tma_pre<8, 6, false, 1>(h, KC_FUSED_S, b, box, pre, epi, red, ts, true); break;
+                default: throw std::runtime_error("pps_debug_fused: variant must be 3, 4, 6 (ring stages) or 16 (6 stages + proxy fence)");
+            }
+        } else {
+            const PrePUpdate<false> pre{u_out, b.r, b.p, b.v, 0, 0};
+            const EpiStoreDot epi{au_out, b.r0};
+            switch (variant) {
+                case 3: launch_tma_pre<8, 3, false>(h, KC_FUSED_P, b, box, pre, epi, red, ts, true); break;
+                case 4: launch_tma_pre<8, 4, false>(h, KC_FUSED_P, b, box, pre, epi, red, ts, true); break;
+                default: throw std::runtime_error("pps_debug_fused: variant must be 3 or 4 for the p kernel");
+            }
+        }
+        compare_bits_kernel<<<148 * 8, 256, 0, h->stream>>>(u_out, u_ref, n, cnt);
+        compare_bits_kernel<<<148 * 8, 256, 0, h->stream>>>(au_out, au_ref, n, cnt + 2);
+        unsigned long long got[4];
+        PPS_CUDA_CHECK(cudaMemcpyAsync(got, cnt, sizeof(got), cudaMemcpyDeviceToHost, h->stream));
+        download_ctl(h);   // synchronises
+        const bool bad_sum = h->ctl_host.sums[0] != sums_ref[0] || (nacc > 1 && h->ctl_host.sums[1] != sums_ref[1]);
+        out[0] += static_cast<long long>(got[0]);
+        out[1] += static_cast<long long>(got[2]);
+        out[2] += bad_sum ? 1 : 0;
+        if (got[0] || got[2] || bad_sum) {
+            out[3]++;
+            if (events < 4 && 8 + 5 * events + 4 < nout) {
+                long long* e = out + 8 + 5 * events++;
+                e[0] = rep; e[1] = static_cast<long long>(got[0]); e[2] = got[0] ? static_cast<long long>(got[1]) : -1;
+                e[3] = static_cast<long long>(got[2]); e[4] = got[2] ? static_cast<long long>(got[3]) : -1;
+            }
+            if (stop_on_bad) break;
+        }
+    }
+    out[4] = b.g.dims.pitch; out[5] = b.g.dims.plane; out[6] = ts.zchunk; out[7] = ts.ctas();
+    cudaFree(cnt);
 }
 
 }  // namespace pps
@@ -2028,6 +2183,24 @@ int pps_allgather(pps_handle* h, const double* in_host, int n, double* out_host)
         PPS_CUDA_CHECK(cudaMemcpyAsync(out_host, dev, sizeof(double) * n * h->world, cudaMemcpyDeviceToHost, h->stream));
         PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     }
+    PPS_API_END
+}
+
+int pps_debug_fused(pps_handle* h, int which, int variant, int reps, long long* out, int nout) {
+    PPS_API_BEGIN
+    if (nout < 8) throw std::runtime_error("pps_debug_fused: out needs at least 8 entries");
+    pps::debug_fused(h, which, variant, reps, out, nout);
+    PPS_API_END
+}
+
+int pps_debug_peek(pps_handle* h, int array, long long offset, int n, double* out) {
+    PPS_API_BEGIN
+    PPS_CUDA_CHECK(cudaSetDevice(h->device));
+    pps::Block& b = h->blocks[0];
+    const double* src[] = {b.s, b.t, b.p2, b.v2, b.r, b.v, b.p, b.r0, b.x};
+    if (array < 0 || array > 8 || src[array] == nullptr) throw std::runtime_error("pps_debug_peek: no such array");
+    if (offset < 0 || offset + n > b.g.dims.total) throw std::runtime_error("pps_debug_peek: out of range");
+    PPS_CUDA_CHECK(cudaMemcpy(out, src[array] + offset, sizeof(double) * n, cudaMemcpyDeviceToHost));
     PPS_API_END
 }
 

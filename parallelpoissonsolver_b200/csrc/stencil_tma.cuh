@@ -156,10 +156,16 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid
             const int so = (warp + 1) * SX + kTmaLead + 2 * lane;
             const int sa = SM::kMainElems + warp * 64 + 2 * lane;
 
+            // Stage 0 (plane kb-1) is released at the END of the first loop iteration, together with stage 1: a ring stage may
+            // only be handed back to the producer after the values read from it have reached registers.  An LDS.128 of a warp
+            // is four 8-lane wavefronts, and a wavefront can still be queued when a later mbarrier.arrive of the same warp has
+            // already been performed (nothing orders the two unless an instruction CONSUMES the loaded registers first).
+            // Releasing stage 0 right after the load let the refill (plane kb-1+STAGES) overtake such a wavefront about once
+            // per 1e6 CTAs at 512^3 (root cause of the round-1 fused-schedule anomaly; tools/fused_debug3.py found the
+            // refilled plane's values in the k-1 neighbour).  In the loop every value read from stage s feeds the stores
+            // that precede the release of s.
             mbar_wait(&full[0], 0);
             double2 cm = *reinterpret_cast<const double2*>(ring + so);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[0]);
             mbar_wait(&full[1 % STAGES], (1 / STAGES) & 1);
             double2 cc = *reinterpret_cast<const double2*>(ring + (1 % STAGES) * SM::kStageElems + so);
             for (int k = kb; k < ke; ++k) {
@@ -185,7 +191,10 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_kernel(const __grid
                     epi(rowoff + k * d.plane, au, cc, ax, m0, m1, acc);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
+                if (lane == 0) {
+                    mbar_arrive(&empty[s]);
+                    if (k == kb) mbar_arrive(&empty[0]);   // plane kb-1: cm has been consumed by now (see the prologue)
+                }
                 cm = cc;
                 cc = cp;
             }
@@ -244,7 +253,8 @@ struct TmaPreSmem {
 
 // The tensor maps are individual __grid_constant__ parameters, exactly like in stencil_tma_kernel (whose maps also change
 // from launch to launch, e.g. the rotating Chebyshev buffers), not members of a wrapper struct.
-template <int BY, int STAGES, bool PARITY, class Pre, class Epi>
+// DBG (diagnostics, pps_debug_fused): bit 0 = cross-proxy fence before a consumer releases a ring stage
+template <int BY, int STAGES, bool PARITY, class Pre, class Epi, int DBG = 0>
 __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_pre_kernel(const __grid_constant__ CUtensorMap map_in0,
                                                                        const __grid_constant__ CUtensorMap map_in1,
                                                                        const __grid_constant__ CUtensorMap map_in2,
@@ -331,10 +341,9 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_pre_kernel(const __
                 return pre.f(a, b, c);
             };
 
+            // stage 0 is released at the end of the first iteration (see stencil_tma_kernel: loads must be consumed first)
             mbar_wait(&full[0], 0);
             double2 cm = eval2(ring, so);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[0]);
             mbar_wait(&full[1 % STAGES], (1 / STAGES) & 1);
             double2 cc = eval2(ring + (1 % STAGES) * SM::kStageElems, so);
             for (int k = kb; k < ke; ++k) {
@@ -360,8 +369,12 @@ __global__ void __launch_bounds__(32 * (BY + 1)) stencil_tma_pre_kernel(const __
                     st2(pre.out + idx, cc, m0, m1);
                     epi(idx, au, cc, ax, m0, m1, acc);
                 }
+                if (DBG & 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
+                if (lane == 0) {
+                    mbar_arrive(&empty[s]);
+                    if (k == kb) mbar_arrive(&empty[0]);
+                }
                 cm = cc;
                 cc = cp;
             }

@@ -61,7 +61,13 @@ CASES = [
     ("qcg40", (1, 1, 1), True), ("qcg40", (2, 2, 1), False),
     ("l48", (1, 1, 1), True), ("l48", (4, 1, 1), True),
     ("l48_cheb", (1, 1, 1), True), ("l48_cheb", (2, 1, 1), False),
+    # the benchmarked configurations and their neighbours: full solves at 128^3 and 256^3, the first 20
+    # iterations at 512^3.  An integer instead of True stores x on the sub-lattice of every s-th global point ("x_sample").
+    # (bench1024_it20 needs ~110 GB of host memory: tools/make_golden_1024.py runs it on the GPU box's host)
+    ("d128", (1, 1, 1), 4), ("d128", (1, 1, 2), False), ("bench256", (2, 2, 2), 8), ("bench256", (1, 1, 8), False),
+    ("bench512_it20", (1, 1, 1), 16), ("bench512_it20", (1, 1, 8), False),
 ]
+BIG = {"d128", "bench256", "bench512_it20", "bench1024_it20"}   # ref_dump writes only the final x (PPS_DUMP_LIGHT)
 
 
 def read_summary(path):
@@ -80,16 +86,22 @@ def read_meta(path):
     return m
 
 
-def assemble(outdir, world, npglobal):
-    g = np.zeros((npglobal[2], npglobal[1], npglobal[0]))
+def assemble(outdir, world, npglobal, stride=1):
+    """global data-range solution; stride s > 1: only the points whose global indices are all multiples of s"""
+    s = stride
+    g = np.zeros(tuple((npglobal[d] + s - 1) // s for d in (2, 1, 0)))
     for r in range(world):
         m = read_meta(f"{outdir}/rank{r}.meta")
         ng, nn, loc = m["nlocal_guards"], m["nlocal_noguards"], m["global_location"]
-        x = np.fromfile(f"{outdir}/rank{r}.x").reshape(ng[2], ng[1], ng[0])
+        x = np.memmap(f"{outdir}/rank{r}.x", dtype=np.float64, mode="r").reshape(ng[2], ng[1], ng[0])
         o = [loc[d] * nn[d] for d in range(3)]
         # axes >= DIM hold one point without guards (blockGrid.hpp:160-182)
         inner = tuple(slice(1, -1) if ng[d] > nn[d] else slice(None) for d in (2, 1, 0))
-        g[o[2]:o[2] + nn[2], o[1]:o[1] + nn[1], o[0]:o[0] + nn[0]] = x[inner]
+        xi = x[inner]
+        first = [(-o[d]) % s for d in range(3)]                    # first local index on the sub-lattice
+        dst = [(o[d] + first[d]) // s for d in range(3)]
+        sub = np.array(xi[first[2]::s, first[1]::s, first[0]::s])
+        g[dst[2]:dst[2] + sub.shape[0], dst[1]:dst[1] + sub.shape[1], dst[0]:dst[0] + sub.shape[2]] = sub
     return g
 
 
@@ -97,7 +109,8 @@ def run_case(name, ranks, store_x):
     c = br.CONFIGS[name]
     exe = os.path.join(br.OUT, "bin", "ref_dump_" + name)
     with tempfile.TemporaryDirectory() as td:
-        r = subprocess.run([exe, *map(str, ranks), td], check=True, capture_output=True, text=True)
+        env = dict(os.environ, PPS_DUMP_LIGHT="1") if name in BIG else None
+        r = subprocess.run([exe, *map(str, ranks), td], check=True, capture_output=True, text=True, env=env)
         s = read_summary(td + "/summary.txt")
         hist = np.fromfile(td + "/history.bin")
         if c["solver"] == "cheb_main":
@@ -117,8 +130,11 @@ def run_case(name, ranks, store_x):
             cheb_rescale_min=500.0 if c.get("rescale_min") is None else float(c["rescale_min"]),
             cheb_rescale_max=1 - 1e-4 if c.get("rescale_max") is None else float(c["rescale_max"]),
         )
-        if store_x:
+        if store_x is True:
             out["x"] = assemble(td, world, c["np"])
+        elif store_x:
+            out["x_sample"] = assemble(td, world, c["np"], int(store_x))
+            out["x_stride"] = int(store_x)
     fn = os.path.join(HERE, f"{name}_{ranks[0]}{ranks[1]}{ranks[2]}.npz")
     np.savez_compressed(fn, **out)
     return fn, out["iters"]

@@ -95,5 +95,25 @@ def pps_global_solution(s, ocfg):
     return assemble_global(fields, blocks, list(ocfg.np))
 
 
+def record_margin(test, **kv):
+    """append the ACHIEVED parity margins of a test to $PPS_MARGINS_FILE (JSON lines) -- VERDICT r1: the margins actually
+    reached must be on record next to the tolerances that are asserted (profiles/r02_parity_margins.jsonl)"""
+    path = os.environ.get("PPS_MARGINS_FILE")
+    if not path:
+        return
+    import json
+    rec = {"test": test}
+    for k, v in kv.items():
+        rec[k] = v.item() if hasattr(v, "item") else v
+    with open(path, "a") as f:
+        f.write(json.dumps(rec) + "\n")
+
+
+def history_margins(hs, hg):
+    """max relative difference of two residual histories through iteration 10 and through iteration 20"""
+    n10, n20 = min(11, len(hs), len(hg)), min(21, len(hs), len(hg))
+    return (float(np.max(np.abs(hs[:n10] - hg[:n10]) / hg[:n10])), float(np.max(np.abs(hs[:n20] - hg[:n20]) / hg[:n20])))
+
+
 def rel_l2(a, b):
     return float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel()))

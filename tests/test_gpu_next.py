@@ -1,20 +1,14 @@
-"""GPU parity tests of the SURVEY.md section 8(f) items that were written after the round-1 GPU budget was spent:
-first-order Neumann closure (orderNeumanBcs = 1), Chebyshev iteration as MAIN solver, nested Krylov preconditioners
-(local BiCGSTAB, local CG + Chebyshev), DIM = 2 and DIM = 1.  The oracle side of each is pinned bit for bit to the unmodified reference on the
-CPU (tests/test_oracle.py); the CUDA side has not run on a GPU yet, so these tests are opt-in until it has:
-
-    PPS_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_next.py -m gpu -x -q
-"""
-import os
-
+"""GPU parity tests of the SURVEY.md section 8(f) items: first-order Neumann closure (orderNeumanBcs = 1), Chebyshev iteration
+as MAIN solver, nested Krylov preconditioners (local BiCGSTAB, local CG + Chebyshev), DIM = 2 and DIM = 1.  The oracle side of
+each is pinned bit for bit to the unmodified reference on the CPU (tests/test_oracle.py).  Verified on B200 in round 2
+(profiles/r02_validation_summary.txt), part of the default GPU suite since."""
 import numpy as np
 import pytest
 
 from oracle import pyoracle as po
 from tests import helpers as H
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PPS_TEST_EXPERIMENTAL") != "1", reason="unverified round-2 paths: set PPS_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 def _pps():
@@ -88,8 +82,10 @@ def test_chebyshev_main_solver(name, arith):
 @pytest.mark.parametrize("precond", [po.PRECOND_BICGSTAB_LOCAL, po.PRECOND_CG_CHEB_LOCAL])
 @pytest.mark.parametrize("shape,bcs", [((24, 20, 28), (0, 1, 0, 1, 0, 1)), ((32, 32, 32), (0, 0, 0, 0, 0, 0))])
 def test_nested_preconditioner_solves_the_block_problem(precond, shape, bcs):
-    """X = M(B) with M a block-local Krylov solve to 1e4 * 1e-10 (solverSetup.hpp:31-32): the result must satisfy the block
-    system to that tolerance (checked with the ORACLE's operator) and agree with the oracle's nested solve"""
+    """X = M(B) with M a block-local Krylov solve to 1e4 * 1e-10 (solverSetup.hpp:31-32): the result must agree with the oracle's
+    nested solve and leave the same block residual (checked with the ORACLE's operator).  Local BiCGSTAB reaches the tolerance;
+    the local CG of inputParam.hpp:29 does NOT on a mixed Dirichlet/Neumann block (the mirrored-ghost operator is not symmetric,
+    CG stagnates and stops at iterMaxPreconditioner = 150, solverSetup.hpp:32) -- the reference's behaviour, reproduced to 13 digits."""
     pps = _pps()
     ocfg = po.make_config(shape, bcs=bcs, precond=precond)
     o = po.Oracle(ocfg)
@@ -106,7 +102,15 @@ def test_nested_preconditioner_solves_the_block_problem(precond, shape, bcs):
     chk = got.copy()
     o.reset_neumann(0, chk)
     res = B - o.apply(0, chk)
-    assert np.linalg.norm(res[box]) <= 2 * ocfg.precond_tolerance * np.linalg.norm(B[box])
+    chk_o = X.copy()
+    o.reset_neumann(0, chk_o)
+    res_o = B - o.apply(0, chk_o)
+    nr, nro, nb = np.linalg.norm(res[box]), np.linalg.norm(res_o[box]), np.linalg.norm(B[box])
+    H.record_margin("nested_preconditioner_block_problem", precond=int(precond), shape=list(shape), residual=nr, residual_oracle=nro,
+                    rel_l2_vs_oracle=H.rel_l2(got[box], X[box]))
+    assert abs(nr - nro) <= 1e-6 * nro + 2e-6 * nb
+    if precond == po.PRECOND_BICGSTAB_LOCAL or not any(bcs):
+        assert nr <= 2 * ocfg.precond_tolerance * nb
     assert H.rel_l2(got[box], X[box]) <= 1e-3
     s.close(); o.close()
 
