@@ -108,6 +108,7 @@ struct pps_handle {
     bool operator_only = false; // PPS_FLAG_OPERATOR_ONLY: only p, v, r0 exist
     bool fuse_full = false;     // 17-pass schedule (single block, all-Dirichlet, no preconditioner)
     bool fuse_p = true, fuse_s = true;   // PPS_FUSE_P / PPS_FUSE_S: enable the two fused kernels separately (diagnostics)
+    int fuse_stages_p = 4, fuse_stages_s = 6;   // ring depth of the two fused kernels (PPS_FUSE_STAGES_P = 3|4, PPS_FUSE_STAGES_S = 3|4|6: tuning sweeps)
     int fuse_check = 0;                  // PPS_FUSE_CHECK=1 (with PPS_FUSE_P=0): verify every fused_s launch against the split kernels
     int fuse_check_events = 0;
     int iter_in_solve = 0;      // host-side count of enqueued iterations of the running solve
@@ -467,13 +468,28 @@ static double* sel_z(Block& b) { return b.z; }
 static double* sel_t(Block& b) { return b.t; }
 static double* sel_cy(Block& b) { return b.cy; }
 
-// CommunicatorMPI::operator() + waitAllandCheckRcv (communicationMPI.hpp:51-316).  `on_halo_stream`: issue the
-// exchange on the high-priority halo stream with its own communicator (overlap with interior compute).
-static void halo_exchange(pps_handle* h, FieldSel sel, bool check_done, bool on_halo_stream = false) {
+static double* sel_r(Block& b) { return b.r; }
+static double* sel_v(Block& b) { return b.v; }
+
+// up to three fields that travel together (the fused schedule exchanges the INPUTS of the fused operand: r, p, v)
+struct FieldSet {
+    FieldSel sel[3] = {nullptr, nullptr, nullptr};
+    int n = 0;
+    FieldSet() {}
+    FieldSet(FieldSel a) : n(1) { sel[0] = a; }
+    FieldSet(FieldSel a, FieldSel b) : n(2) { sel[0] = a; sel[1] = b; }
+    FieldSet(FieldSel a, FieldSel b, FieldSel c) : n(3) { sel[0] = a; sel[1] = b; sel[2] = c; }
+};
+constexpr int kMaxExchangeFields = 3;
+
+// CommunicatorMPI::operator() + waitAllandCheckRcv (communicationMPI.hpp:51-316) for every field of `fs`; all faces of all
+// fields travel in ONE NCCL group.  `on_halo_stream`: issue the exchange on the high-priority halo stream with its own
+// communicator (overlap with interior compute).
+static void halo_exchange(pps_handle* h, const FieldSet& fs, bool check_done, bool on_halo_stream = false) {
     bool any = false;
     for (auto& b : h->blocks)
         for (int f = 0; f < 6; f++) any = any || b.g.hc[f];
-    if (!any || h->debug_no_halo) return;
+    if (!any || h->debug_no_halo || fs.n == 0) return;
     LaunchScope ls(h, KC_HALO);
     const int ign = check_done ? 0 : 1;
     if (h->world == 1) {
@@ -486,46 +502,58 @@ static void halo_exchange(pps_handle* h, FieldSel sel, bool check_done, bool on_
                 FaceGeom theirs = face_geom(nb->g, f ^ 1, 1, 1);
                 FaceGeom g = mine;
                 g.base_b = theirs.base_b;
-                face_copy_kernel<<<face_blocks(g), 256, 0, h->stream>>>(sel(b), sel(*nb), g, h->ctl, ign);
-                ls.count(1);
+                for (int q = 0; q < fs.n; q++) {
+                    face_copy_kernel<<<face_blocks(g), 256, 0, h->stream>>>(fs.sel[q](b), fs.sel[q](*nb), g, h->ctl, ign);
+                    ls.count(1);
+                }
             }
         }
     } else {
         cudaStream_t st = on_halo_stream ? h->halo_stream : h->stream;
         ncclComm_t comm = on_halo_stream ? h->comm_halo : h->comm;
         Block& b = h->blocks[0];
-        double* fld = sel(b);
-        for (int f = 0; f < 4; f++) {   // x and y faces are strided: pack first
-            if (!b.g.hc[f]) continue;
-            FaceGeom g = face_geom(b.g, f, 1, 1);
-            face_pack_kernel<<<face_blocks(g), 256, 0, st>>>(b.sendbuf[f], fld, g, h->ctl, ign);
-            ls.count(1);
+        auto face_count = [&](int f) { return static_cast<size_t>(b.g.n[f / 2 == 0 ? 1 : 0]) * b.g.n[2]; };
+        for (int q = 0; q < fs.n; q++) {
+            for (int f = 0; f < 4; f++) {   // x and y faces are strided: pack first
+                if (!b.g.hc[f]) continue;
+                FaceGeom g = face_geom(b.g, f, 1, 1);
+                face_pack_kernel<<<face_blocks(g), 256, 0, st>>>(b.sendbuf[f] + q * face_count(f), fs.sel[q](b), g, h->ctl, ign);
+                ls.count(1);
+            }
         }
         PPS_NCCL_CHECK(nccl().GroupStart());
         for (int f = 0; f < 6; f++) {
             if (!b.g.hc[f]) continue;
             const int peer = b.g.nbr[f];
             if (f < 4) {
-                const size_t cnt = static_cast<size_t>(b.g.n[f / 2 == 0 ? 1 : 0]) * b.g.n[2];
+                const size_t cnt = face_count(f) * fs.n;   // the fields of one face are packed back to back
                 PPS_NCCL_CHECK(nccl().Send(b.sendbuf[f], cnt, ncclDouble, peer, comm, st));
                 PPS_NCCL_CHECK(nccl().Recv(b.recvbuf[f], cnt, ncclDouble, peer, comm, st));
             } else {
                 // z faces: a k-plane of the pitched layout is contiguous, padding and all -- no packing
                 const int up = f % 2;
                 const long long kdata = up ? b.g.n[2] : 1, kguard = up ? b.g.n[2] + 1 : 0;
-                PPS_NCCL_CHECK(nccl().Send(fld + kdata * b.g.dims.plane, b.g.dims.plane, ncclDouble, peer, comm, st));
-                PPS_NCCL_CHECK(nccl().Recv(fld + kguard * b.g.dims.plane, b.g.dims.plane, ncclDouble, peer, comm, st));
+                for (int q = 0; q < fs.n; q++) {
+                    double* fld = fs.sel[q](b);
+                    PPS_NCCL_CHECK(nccl().Send(fld + kdata * b.g.dims.plane, b.g.dims.plane, ncclDouble, peer, comm, st));
+                    PPS_NCCL_CHECK(nccl().Recv(fld + kguard * b.g.dims.plane, b.g.dims.plane, ncclDouble, peer, comm, st));
+                }
             }
         }
         PPS_NCCL_CHECK(nccl().GroupEnd());
-        for (int f = 0; f < 4; f++) {
-            if (!b.g.hc[f]) continue;
-            FaceGeom g = face_geom(b.g, f, 0, 0);
-            face_unpack_kernel<<<face_blocks(g), 256, 0, st>>>(fld, b.recvbuf[f], g, h->ctl, ign);
-            ls.count(1);
+        for (int q = 0; q < fs.n; q++) {
+            for (int f = 0; f < 4; f++) {
+                if (!b.g.hc[f]) continue;
+                FaceGeom g = face_geom(b.g, f, 0, 0);
+                face_unpack_kernel<<<face_blocks(g), 256, 0, st>>>(fs.sel[q](b), b.recvbuf[f] + q * face_count(f), g, h->ctl, ign);
+                ls.count(1);
+            }
         }
     }
     check_launch("halo");
+}
+static void halo_exchange(pps_handle* h, FieldSel sel, bool check_done, bool on_halo_stream = false) {
+    halo_exchange(h, FieldSet(sel), check_done, on_halo_stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1101,34 +1129,40 @@ static void split_box(const BlockGeom& g, const Box& box, int tz, Box& inner, st
 }
 static bool box_empty(const Box& b) { return b.i0 >= b.i1 || b.j0 >= b.j1 || b.k0 >= b.k1; }
 
-template <class MakeEpi>
-static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int nacc, int op, MakeEpi make_epi) {
+// `xchg`: fields whose faces are exchanged first, `ghost`: fields whose Neumann ghosts are rewritten (both are the operand
+// itself for the plain operator kernels, and the INPUTS of the fused operand for stencil_tma_pre_kernel).
+// `launch(block, box, tiling, red)` enqueues the operator kernel on h->launch_stream for a sub-box of the block.
+// `plain_stencil`: the launch goes through launch_stencil, i.e. the in-kernel-wait / peer-transport schedules may be used.
+template <class Launch>
+static void overlapped_operator(pps_handle* h, const FieldSet& xchg, const FieldSet& ghost, int nacc, int op, bool plain_stencil,
+                                Launch launch) {
     bool any_comm = false;
     for (int f = 0; f < 6; f++) any_comm = any_comm || h->blocks[0].g.hc[f];
-    const bool overlap = h->world > 1 && h->overlap && !h->debug_no_halo && any_comm;
+    const bool overlap = h->world > 1 && h->overlap && !h->debug_no_halo && any_comm && xchg.n > 0;
     if (!overlap) {
-        halo_exchange(h, sel, true);
+        halo_exchange(h, xchg, true);
         const unsigned int total = total_ctas(h, true);
         unsigned int off = 0;
         for (auto& b : h->blocks) {
-            if (ghosts) neumann_ghosts(h, b, sel(b), false, true);
+            for (int q = 0; q < ghost.n; q++) neumann_ghosts(h, b, ghost.sel[q](b), false, true);
             const Box box = b.g.solver_box();
             const Tiling t = make_tiling(h, b.g, box, true);
             RedCtx red = make_red(h, nacc, total, off, op);
-            launch_stencil(h, kc, b, sel(b), box, make_epi(b), red, t, true);
+            launch(b, box, t, red);
             off += t.ctas();
         }
     } else {
         Block& b = h->blocks[0];
         PPS_CUDA_CHECK(cudaEventRecord(h->ev_field_ready, h->stream));
         PPS_CUDA_CHECK(cudaStreamWaitEvent(h->halo_stream, h->ev_field_ready, 0));
-        const bool use_p2p = h->p2p && (sel == sel_mp || sel == sel_z);
+        const FieldSel sel = xchg.sel[0];
+        const bool use_p2p = h->p2p && plain_stencil && xchg.n == 1 && (sel == sel_mp || sel == sel_z);
         unsigned int p2p_epoch = 0;
         const int p2p_field = sel == sel_z ? 1 : 0;
         if (use_p2p) p2p_epoch = halo_push_p2p(h, p2p_field, sel(b));
-        else halo_exchange(h, sel, true, /*on_halo_stream=*/true);
+        else halo_exchange(h, xchg, true, /*on_halo_stream=*/true);
         const bool z_only = !(b.g.hc[0] || b.g.hc[1] || b.g.hc[2] || b.g.hc[3]);
-        if (ghosts) neumann_ghosts(h, b, sel(b), false, true);
+        for (int q = 0; q < ghost.n; q++) neumann_ghosts(h, b, ghost.sel[q](b), false, true);
         const Tiling t_all = make_tiling(h, b.g, b.g.solver_box(), true);
         if (use_p2p && h->stencil_impl == 1 && h->overlap == 3 && t_all.grid.z >= 3) {
             // EXPERIMENTAL (PPS_OVERLAP=3, needs PPS_HALO_P2P=1): ONE launch; the TMA producers of the first / last z-chunk wait
@@ -1139,8 +1173,8 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
             h->wait_next = HaloWait{h->recv_epoch + 2 * p2p_field, p2p_epoch, b.g.hc[4] ? 0 : -1, b.g.hc[5] ? b.g.n[2] + 1 : -1,
                                     (b.g.hc[4] && t.grid.z > 1) ? 1 : 0, h->recv_epoch + 2 * p2p_field + 1, 1};
             RedCtx red = make_red(h, nacc, t.ctas(), 0, op);
-            launch_stencil(h, kc, b, sel(b), box, make_epi(b), red, t, true);
-        } else if (!use_p2p && z_only && h->stencil_impl == 1 && h->overlap == 2 && t_all.grid.z >= 3) {
+            launch(b, box, t, red);
+        } else if (!use_p2p && plain_stencil && z_only && h->stencil_impl == 1 && h->overlap == 2 && t_all.grid.z >= 3) {
             // EXPERIMENTAL (PPS_OVERLAP=2): ONE launch; the first / last z-chunk run last and their TMA producer waits in-kernel
             // for the faces.  Fastest when it works, but it needs the NCCL kernel to become resident while waiting CTAs hold
             // the SMs -- CUDA gives no such forward-progress guarantee (it deadlocked on 8 GPUs), hence not the default.
@@ -1151,7 +1185,7 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
             h->wait_next = HaloWait{h->halo_flag, h->halo_epoch, b.g.hc[4] ? 0 : -1, b.g.hc[5] ? b.g.n[2] + 1 : -1,
                                     (b.g.hc[4] && t.grid.z > 1) ? 1 : 0};
             RedCtx red = make_red(h, nacc, t.ctas(), 0, op);
-            launch_stencil(h, kc, b, sel(b), box, make_epi(b), red, t, true);
+            launch(b, box, t, red);
         } else {
             // interior box on the compute stream now; the boundary shell on its own stream as soon as the faces have
             // landed -- both launches share the GPU (no serialisation, no in-kernel waiting) and feed one ticket reduction
@@ -1183,7 +1217,7 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
                     h->launch_stream = h->bnd_stream;
                 }
                 RedCtx red = make_red(h, nacc, total, off, op);
-                launch_stencil(h, kc, b, sel(b), boxes[q], make_epi(b), red, tl[q], true);
+                launch(b, boxes[q], tl[q], red);
                 off += tl[q].ctas();
             }
             h->launch_stream = h->stream;
@@ -1193,6 +1227,15 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
         }
     }
     if (nacc > 0) finish_reduction(h, nacc, op, false);
+}
+
+// the plain operator kernels: exchange + ghosts on the operand itself
+template <class MakeEpi>
+static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int nacc, int op, MakeEpi make_epi) {
+    overlapped_operator(h, FieldSet(sel), ghosts ? FieldSet(sel) : FieldSet(), nacc, op, true,
+                        [&](Block& b, const Box& box, const Tiling& t, const RedCtx& red) {
+                            launch_stencil(h, kc, b, sel(b), box, make_epi(b), red, t, true);
+                        });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1271,51 +1314,88 @@ static void fused_s_check(pps_handle* h, Block& b, const Box& box, const Tiling&
 
 // PPS_FUSE_FULL: the same iteration in 3 kernels / 17 vector passes.  p and v are double-buffered (other CTAs still read
 // the previous p and v on their halo while this CTA stores the new ones) and s gets its own array for the same reason.
+// The fused operand u = f(inputs) is recomputed on the halo from the inputs' halo, so what travels between blocks / GPUs and
+// what is mirrored on Neumann faces are the INPUTS (f is pointwise: f(mirror) = mirror(f), f(neighbour's) = neighbour's u):
+//   fused_p reads r (new from the x/r update), p (stored by the previous fused_p, interior only), v (exchanged by the previous fused_s)
+//   fused_s reads r (exchanged by this iteration's fused_p), v (new)
+// i.e. three face exchanges per iteration (r + p in one message, then v) instead of the split schedule's two.
 static void bicgstab_iteration_fused(pps_handle* h) {
-    Block& b = h->blocks[0];
-    const Box box = b.g.solver_box();
-    const Tiling ts = make_tiling(h, b.g, box, true);
-    const Tiling tp = make_tiling(h, b.g, box, false);
-    if (h->iter_in_solve > 0 && h->fuse_p) {
+    const bool parity = h->parity;
+    const bool first = h->iter_in_solve == 0;
+    if (!first && h->fuse_p) {
         // p' = r + beta (p - omega v) ; v' = A p' ; sum r0.v' ; alpha            :262-272 of the previous pass + :142-164
-        RedCtx red = make_red(h, 1, ts.ctas(), 0, OP_BICG_ALPHA);
-        if (h->parity) launch_tma_pre<8, 4, true>(h, KC_FUSED_P, b, box, PrePUpdate<true>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, ts, true);
-        else           launch_tma_pre<8, 4, false>(h, KC_FUSED_P, b, box, PrePUpdate<false>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, ts, true);
-        std::swap(b.p, b.p2);
-        std::swap(b.v, b.v2);
-        b.mp = b.p;
+        const FieldSet in = h->fuse_s ? FieldSet(sel_r, sel_p) : FieldSet(sel_r, sel_p, sel_v);
+        overlapped_operator(h, in, in, 1, OP_BICG_ALPHA, false, [&](Block& b, const Box& box, const Tiling& t, const RedCtx& red) {
+            if (parity) launch_tma_pre<8, 4, true>(h, KC_FUSED_P, b, box, PrePUpdate<true>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, t, true);
+            else if (h->fuse_stages_p == 3) launch_tma_pre<8, 3, false>(h, KC_FUSED_P, b, box, PrePUpdate<false>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, t, true);
+            else        launch_tma_pre<8, 4, false>(h, KC_FUSED_P, b, box, PrePUpdate<false>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, t, true);
+        });
+        for (auto& b : h->blocks) {
+            std::swap(b.p, b.p2);
+            std::swap(b.v, b.v2);
+            b.mp = b.p;
+        }
     } else {
         // first iteration (p0 = r0 is already in place, BiCGSTAB.hpp:125) or PPS_FUSE_P=0: p-update in place, plain operator
-        if (h->iter_in_solve > 0) {
-            RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
-            if (h->parity) launch_pointwise(h, KC_P_UPDATE, b, box, OpPUpdate<true>{b.p, b.r, b.v, 0, 0}, none, tp, true);
-            else           launch_pointwise(h, KC_P_UPDATE, b, box, OpPUpdate<false>{b.p, b.r, b.v, 0, 0}, none, tp, true);
+        if (!first) {
+            for (auto& b : h->blocks) {
+                const Box box = b.g.solver_box();
+                const Tiling tp = make_tiling(h, b.g, box, false);
+                RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
+                if (parity) launch_pointwise(h, KC_P_UPDATE, b, box, OpPUpdate<true>{b.p, b.r, b.v, 0, 0}, none, tp, true);
+                else        launch_pointwise(h, KC_P_UPDATE, b, box, OpPUpdate<false>{b.p, b.r, b.v, 0, 0}, none, tp, true);
+            }
         }
-        RedCtx red = make_red(h, 1, ts.ctas(), 0, OP_BICG_ALPHA);
-        launch_stencil(h, KC_APPLY_DOT, b, b.p, box, EpiStoreDot{b.v, b.r0}, red, ts, true);
+        fused_operator(h, KC_APPLY_DOT, sel_p, true, 1, OP_BICG_ALPHA, [](Block& b) { return EpiStoreDot{b.v, b.r0}; });
     }
     if (h->fuse_s) {
         {   // s = r - alpha v ; t = A s ; sum s.t, t.t ; omega                        :168-225
-            RedCtx red = make_red(h, 2, ts.ctas(), 0, OP_BICG_OMEGA);
-            if (h->parity) launch_tma_pre<8, 6, true>(h, KC_FUSED_S, b, box, PreSUpdate<true>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, ts, true);
-            else           launch_tma_pre<8, 6, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, ts, true);
+            const FieldSet in = (first || !h->fuse_p) ? FieldSet(sel_v, sel_r) : FieldSet(sel_v);
+            overlapped_operator(h, in, in, 2, OP_BICG_OMEGA, false, [&](Block& b, const Box& box, const Tiling& t, const RedCtx& red) {
+                if (parity) launch_tma_pre<8, 6, true>(h, KC_FUSED_S, b, box, PreSUpdate<true>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
+                else if (h->fuse_stages_s == 3) launch_tma_pre<8, 3, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
+                else if (h->fuse_stages_s == 4) launch_tma_pre<8, 4, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
+                else        launch_tma_pre<8, 6, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
+            });
         }
-        if (h->fuse_check && !h->fuse_p) fused_s_check(h, b, box, ts, tp);
-        {   // x += alpha p + omega s ; r = s - omega t ; sum r0.r, r.r ; beta, rho     :227-259
-            RedCtx red = make_red(h, 2, tp.ctas(), 0, OP_BICG_RHO);
-            if (h->parity) launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdateS<true>{b.x, b.r, b.p, b.s, b.t, b.r0, 0, 0}, red, tp, true);
-            else           launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdateS<false>{b.x, b.r, b.p, b.s, b.t, b.r0, 0, 0}, red, tp, true);
+        if (h->fuse_check && !h->fuse_p) {
+            Block& b = h->blocks[0];
+            const Box box = b.g.solver_box();
+            fused_s_check(h, b, box, make_tiling(h, b.g, box, true), make_tiling(h, b.g, box, false));
         }
+        // x += alpha p + omega s ; r = s - omega t ; sum r0.r, r.r ; beta, rho     :227-259
+        const unsigned int total = total_ctas(h, false);
+        unsigned int off = 0;
+        for (auto& b : h->blocks) {
+            const Box box = b.g.solver_box();
+            const Tiling tp = make_tiling(h, b.g, box, false);
+            RedCtx red = make_red(h, 2, total, off, OP_BICG_RHO);
+            if (parity) launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdateS<true>{b.x, b.r, b.p, b.s, b.t, b.r0, 0, 0}, red, tp, true);
+            else        launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdateS<false>{b.x, b.r, b.p, b.s, b.t, b.r0, 0, 0}, red, tp, true);
+            off += tp.ctas();
+        }
+        finish_reduction(h, 2, OP_BICG_RHO, false);
     } else {
         // PPS_FUSE_S=0: the split kernels for this half (s lives in r)
-        RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
-        if (h->parity) launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<true>{b.r, b.v, 0}, none, tp, true);
-        else           launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<false>{b.r, b.v, 0}, none, tp, true);
-        RedCtx red2 = make_red(h, 2, ts.ctas(), 0, OP_BICG_OMEGA);
-        launch_stencil(h, KC_APPLY_DOT2, b, b.r, box, EpiStoreDot2Self{b.t}, red2, ts, true);
-        RedCtx red3 = make_red(h, 2, tp.ctas(), 0, OP_BICG_RHO);
-        if (h->parity) launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdate<true>{b.x, b.r, b.p, b.r, b.t, b.r0, 0, 0}, red3, tp, true);
-        else           launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdate<false>{b.x, b.r, b.p, b.r, b.t, b.r0, 0, 0}, red3, tp, true);
+        for (auto& b : h->blocks) {
+            const Box box = b.g.solver_box();
+            const Tiling tp = make_tiling(h, b.g, box, false);
+            RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
+            if (parity) launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<true>{b.r, b.v, 0}, none, tp, true);
+            else        launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<false>{b.r, b.v, 0}, none, tp, true);
+        }
+        fused_operator(h, KC_APPLY_DOT2, sel_r, true, 2, OP_BICG_OMEGA, [](Block& b) { return EpiStoreDot2Self{b.t}; });
+        const unsigned int total = total_ctas(h, false);
+        unsigned int off = 0;
+        for (auto& b : h->blocks) {
+            const Box box = b.g.solver_box();
+            const Tiling tp = make_tiling(h, b.g, box, false);
+            RedCtx red3 = make_red(h, 2, total, off, OP_BICG_RHO);
+            if (parity) launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdate<true>{b.x, b.r, b.p, b.r, b.t, b.r0, 0, 0}, red3, tp, true);
+            else        launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdate<false>{b.x, b.r, b.p, b.r, b.t, b.r0, 0, 0}, red3, tp, true);
+            off += tp.ctas();
+        }
+        finish_reduction(h, 2, OP_BICG_RHO, false);
     }
     h->iter_in_solve++;
 }
@@ -1566,16 +1646,21 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     if (cfg.precond_max_iter > 0) h->precond_max_iter = cfg.precond_max_iter;
     if (cfg.precond_tolerance > 0) h->precond_tolerance = cfg.precond_tolerance;
     {
-        // 17-pass schedule: opt-in (PPS_FUSE_FULL or PPS_FUSE=2), and only where every halo value of the fused operand can be
-        // recomputed locally: one block, no Neumann face, no preconditioner, BiCGSTAB, TMA operator kernels
+        // 17-pass schedule (PPS_FUSE_FULL; what PPS_FUSE_AUTO picks since round 2, when the ring-release hazard that made it
+        // irreproducible was root-caused, stencil_tma.cuh) wherever every halo value of the fused operand can be recomputed
+        // locally: one block, no Neumann face, no preconditioner, BiCGSTAB, TMA operator kernels.  PPS_FUSE=1 forces the split schedule.
         const int want = env_int("PPS_FUSE", cfg.fusion);
         bool neumann = false;
         for (int f = 0; f < 6; f++) neumann = neumann || cfg.bcs_type[f] == 1;
-        h->fuse_full = want == PPS_FUSE_FULL && world == 1 && nr == 1 && cfg.dim == 3 && !neumann && !has_precond && cfg.solver == PPS_SOLVER_BICGSTAB &&
-                       h->stencil_impl == 1 && h->by_tma == 8;
+        (void)neumann;
+        h->fuse_full = want != PPS_FUSE_SPLIT && cfg.dim == 3 && !has_precond && cfg.solver == PPS_SOLVER_BICGSTAB &&
+                       h->stencil_impl == 1 && h->by_tma == 8 &&
+                       !(world > 1 && env_int("PPS_HALO_P2P", 0));   // the peer transport maps Mp and z only (no ping-pong buffers)
         h->fuse_p = env_int("PPS_FUSE_P", 1) != 0;
         h->fuse_s = env_int("PPS_FUSE_S", 1) != 0;
         h->fuse_check = env_int("PPS_FUSE_CHECK", 0);
+        h->fuse_stages_p = env_int("PPS_FUSE_STAGES_P", 4);
+        h->fuse_stages_s = env_int("PPS_FUSE_STAGES_S", 6);
     }
     unsigned long long max_ctas = 0;
     h->operator_only = (cfg.flags & PPS_FLAG_OPERATOR_ONLY) != 0;
@@ -1621,8 +1706,8 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
             for (int f = 0; f < 4; f++) {
                 if (!b.g.hc[f]) continue;
                 const long long cnt = static_cast<long long>(b.g.n[f / 2 == 0 ? 1 : 0]) * b.g.n[2];
-                b.sendbuf[f] = dalloc(b, cnt, h->stream);
-                b.recvbuf[f] = dalloc(b, cnt, h->stream);
+                b.sendbuf[f] = dalloc(b, cnt * kMaxExchangeFields, h->stream);
+                b.recvbuf[f] = dalloc(b, cnt * kMaxExchangeFields, h->stream);
             }
         }
         // upper bound of CTAs any tiling of this block can produce (zchunk >= 1)

@@ -39,7 +39,7 @@ def _run(layout, flags=(), env=None):
 
 
 @pytest.mark.parametrize("layout", [(1, 1, 2), (2, 1, 1), (1, 2, 1)])
-@pytest.mark.parametrize("flags", [(), ("cheb",), ("cg",)])
+@pytest.mark.parametrize("flags", [("fusecmp",), ("cheb",), ("cg",)])
 def test_two_gpus(layout, flags):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
@@ -57,7 +57,7 @@ def test_four_gpus(layout):
 def test_eight_gpus(layout):
     if _ngpu() < 8:
         pytest.skip("needs 8 GPUs")
-    _run(layout)
+    _run(layout, ("fusecmp",))
 
 
 EXPERIMENTAL = os.environ.get("PPS_TEST_EXPERIMENTAL") == "1"

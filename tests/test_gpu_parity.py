@@ -119,11 +119,19 @@ def _reference_iteration_spread(o):
 
 
 def _assert_iterations(got, lo, hi):
-    assert 0.9 * lo - 2 <= got <= 1.06 * hi + 2, (got, lo, hi)
+    """`lo`, `hi`: the reference's count on the few rank layouts the fixtures hold.  The window around them is the reference's
+    OWN measured spread over 20 rank layouts of one problem (profiles/r02_reference_iteration_spread.jsonl, made by
+    tools/ref_iteration_spread.py from the unmodified reference): 79..85 at 32^3 (7.6 %), 154..170 at 64^3 (10.4 %),
+    295..357 at 128^3 (21 %) -- a layout changes only the summation order of the dot products, exactly what separates the
+    CUDA path from the reference.  north_star's "+-2 iterations" is therefore not a property the reference has with
+    respect to itself at tolerance 1e-8; what is asked here is "inside the reference's own band" (15 % around the sampled counts)."""
+    assert 0.85 * lo - 2 <= got <= 1.15 * hi + 2, (got, lo, hi)
 
 
 # lock-step bar of the residual history (relative), through iteration 10 / 20: SURVEY.md section 7 "Hard parts" (ii)
-HIST_TOL10, HIST_TOL20 = 1e-10, 1e-6
+# Achieved on B200 over the 60 (config, layout) cases of this file (gpurun_out -> profiles/r02_parity_margins.jsonl): worst 6.1e-12
+# through iteration 10, 3.6e-8 through iteration 20 -- the SURVEY's own numbers (1e-11 / 1e-7) are asked.
+HIST_TOL10, HIST_TOL20 = 1e-11, 1e-7
 
 
 def _check_solve_against_oracle(o, s, hist_tol10=HIST_TOL10, hist_tol20=HIST_TOL20, iter_slack=None, sol_tol=2e-6):
@@ -395,27 +403,71 @@ def test_config_errors():
     s.close()
 
 
-@pytest.mark.parametrize("np_", [(32, 32, 32), (70, 33, 41)])
+FUSED_CASES = [
+    ((32, 32, 32), (1, 1, 1), (0, 0, 0, 0, 0, 0)),
+    ((70, 33, 41), (1, 1, 1), (0, 0, 0, 0, 0, 0)),
+    ((24, 20, 28), (1, 1, 1), (0, 1, 0, 1, 0, 1)),      # Neumann faces: the inputs of the fused operand are mirrored
+    ((67, 20, 12), (1, 1, 1), (1, 0, 1, 0, 0, 1)),
+    ((24, 20, 28), (1, 1, 2), (0, 0, 0, 0, 0, 0)),      # several blocks: the inputs travel between blocks (z-slabs)
+    ((24, 20, 28), (2, 1, 1), (0, 1, 0, 1, 0, 1)),      # x faces + Neumann
+    ((24, 20, 28), (1, 2, 1), (1, 1, 0, 1, 1, 0)),
+    ((24, 20, 28), (2, 2, 2), (0, 1, 0, 1, 0, 1)),
+]
+
+
+@pytest.mark.parametrize("np_,nranks,bcs", FUSED_CASES)
 @pytest.mark.parametrize("arith", ["fast", "parity"])
-def test_fused_schedule_is_bitwise_identical_to_split(np_, arith):
-    """PPS_FUSE_FULL (s- and p-updates recomputed inside the operator kernels, 17 passes) runs the same arithmetic in
-    the same reduction order as the 19-pass schedule: residual history, iteration count and solution must be equal
-    to the last bit."""
+def test_fused_schedule_is_bitwise_identical_to_split(np_, nranks, bcs, arith):
+    """PPS_FUSE_FULL (s- and p-updates recomputed inside the operator kernels, 17 passes; the AUTO default for
+    unpreconditioned BiCGSTAB) runs the same arithmetic in the same reduction order as the 19-pass schedule: residual
+    history, iteration count and solution must be equal to the last bit -- on one block, with Neumann faces (the inputs
+    of the fused operand are mirrored instead of the operand) and across blocks (the inputs are exchanged)."""
     pps = _pps()
     a = pps.ARITH_PARITY if arith == "parity" else pps.ARITH_FAST
-    o, s_split = _pair(np_, arithmetic=a, fusion=pps.FUSE_SPLIT)
+    o, s_split = _pair(np_, nranks=nranks, bcs=bcs, arithmetic=a, fusion=pps.FUSE_SPLIT)
     o.set_problem()
     H.hand_over_problem(o, s_split)
     s_split.solve()
     s_full = pps.PoissonSolver(H.pps_config_from_oracle(o.cfg, arithmetic=a, fusion=pps.FUSE_FULL))
     H.hand_over_problem(o, s_full)
     s_full.solve()
-    names = [k["name"] for k in s_full.kernel_stats()] if False else None
-    assert s_full.iterations == s_split.iterations
+    assert s_full.iterations == s_split.iterations > 10
     assert np.array_equal(s_full.history(), s_split.history())
-    assert np.array_equal(s_full.get_solution(0), s_split.get_solution(0))
-    assert s_full.launch_count < s_split.launch_count          # 3 instead of 5 kernels per iteration
+    for r in range(o.world):
+        assert np.array_equal(s_full.get_solution(r), s_split.get_solution(r))
+    # 3 instead of 5 compute kernels per iteration (several blocks: one more face exchange per iteration)
+    if o.world == 1:
+        assert s_full.launch_count < s_split.launch_count
+    names = {k["name"]: k["launches"] for k in s_full.kernel_stats()}
+    assert names.get("fused_s(s=r-alpha*v, t=A*s, s.t, t.t)", 0) >= s_full.iterations * o.world
     s_full.close(); s_split.close(); o.close()
+
+
+def test_fused_schedule_repeat_solves_are_reproducible():
+    """Regression for the round-1 anomaly (three converged solves on ONE handle at 512^3 gave 1203 / 1459 / 1242 iterations
+    with the fused schedule): a ring stage of stencil_tma_pre_kernel was handed back to the TMA producer before the
+    consumer's shared-memory loads from it had completed, about once per 1e6 CTAs.  256^3 launches ~1.3e6 fused CTAs per
+    solve: three solves on one handle must agree with each other and with the split schedule to the last bit."""
+    pps = _pps()
+    n = 256
+    o, s_split = _pair((n, n, n), max_iter=3000, fusion=pps.FUSE_SPLIT)
+    o.set_problem()
+    H.hand_over_problem(o, s_split)
+    s_split.solve()
+    want_hist, want_it = s_split.history().copy(), s_split.iterations
+    s_split.close()
+    s = pps.PoissonSolver(H.pps_config_from_oracle(o.cfg, fusion=pps.FUSE_AUTO))
+    H.hand_over_problem(o, s)
+    s.save_fields()
+    for rep in range(3):
+        if rep:
+            s.restore_fields()
+        s.set_profiling(rep == 1)          # the anomaly was first seen on a profiled repeat solve
+        s.solve()
+        assert s.iterations == want_it, (rep, s.iterations, want_it)
+        assert np.array_equal(s.history(), want_hist), rep
+        assert abs(s.error_operator - s.error_iteration) <= 1e-6 * s.error_iteration
+    s.close(); o.close()
 
 
 def test_batched_neumann_ghosts_bitwise(monkeypatch):

@@ -50,16 +50,29 @@ def main():
     o = po.Oracle(ocfg)
     o.set_problem()
 
-    t = torch.zeros(128, dtype=torch.uint8, device=dev)
-    if rank == 0:
-        t.copy_(torch.frombuffer(bytearray(pps.get_unique_id()), dtype=torch.uint8))
-    dist.broadcast(t, 0)
-    uid = bytes(t.cpu().numpy().tobytes())
+    def solve_with(fusion):
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(pps.get_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().numpy().tobytes())
+        s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, device=local, fusion=fusion), rank=rank, world_size=world, unique_id=uid)
+        H.hand_over_problem(o, s, ranks=[rank])
+        s.solve()
+        return s, s.get_solution(rank)
 
-    s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, device=local), rank=rank, world_size=world, unique_id=uid)
-    H.hand_over_problem(o, s, ranks=[rank])
-    s.solve()
-    x = s.get_solution(rank)
+    s, x = solve_with(pps.FUSE_AUTO)
+    fused_equals_split = None
+    if "fusecmp" in flags:
+        # the 17-pass schedule (AUTO for unpreconditioned BiCGSTAB) against the 19-pass one on the same ranks: same bits
+        s2, x2 = solve_with(pps.FUSE_SPLIT)
+        same = bool(np.array_equal(s.history(), s2.history()) and np.array_equal(x, x2) and s.iterations == s2.iterations)
+        names = [k["name"] for k in s.kernel_stats()]
+        same = same and any(n.startswith("fused_s") for n in names)
+        f = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        fused_equals_split = bool(int(f.item()))
+        s2.close()
 
     # gather the per-rank data-range blocks on rank 0
     mine = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
@@ -78,8 +91,15 @@ def main():
         # guard planes after the final halo exchange (BiCGSTAB.hpp:317-321): my z- / x- guard = neighbour's data
         out = dict(layout=[px, py, pz], flags=flags, iters=s.iterations, iters_oracle=o.iters, norm_b_rel=abs(s.norm_b - o.norm_b) / o.norm_b,
                    hist10=d10, hist20=d20, sol_rel_l2=rel, true_residual=s.error_operator, seconds=s.solver_seconds)
-        ok = (out["norm_b_rel"] <= 1e-13 and d10 <= 1e-10 and d20 <= 1e-6 and rel <= 2e-6 and
-              0.9 * o.iters - 2 <= s.iterations <= 1.06 * o.iters + 2 and s.error_operator < 1.5e-8)
+        out["fused_equals_split"] = fused_equals_split
+        # same bars as tests/test_gpu_parity.py (history 1e-11 / 1e-7, iterations inside the reference's own 15 % band)
+        ok = (out["norm_b_rel"] <= 1e-13 and d10 <= 1e-11 and d20 <= 1e-7 and rel <= 2e-6 and
+              0.85 * o.iters - 2 <= s.iterations <= 1.15 * o.iters + 2 and s.error_operator < 1.5e-8 and
+              fused_equals_split is not False)
+        try:
+            H.record_margin("multi_gpu_vs_oracle", **{k: v for k, v in out.items() if k != "flags"}, flags=list(flags))
+        except Exception:
+            pass
         out["ok"] = bool(ok)
         print(json.dumps(out), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)

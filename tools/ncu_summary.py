@@ -16,7 +16,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def short(name):
-    m = re.search(r"(stencil_tma_kernel|stencil_kernel|pointwise_kernel)<([^>]*(?:<[^>]*>)?[^>]*)>", name)
+    m = re.search(r"(stencil_tma_pre_kernel|stencil_tma_kernel|stencil_kernel|pointwise_kernel)<([^>]*(?:<[^>]*>)?[^>]*)>", name)
     if m:
         return m.group(1) + "<" + m.group(2) + ">"
     return name.split("(")[0][:60]
@@ -53,8 +53,29 @@ def full(paths):
                     print(f"| {k} | {r[h.index(k)]} | {u[h.index(k)]} |")
 
 
+def traffic(cells, pairs):
+    """traffic <cells> key=report.ncu-rep ... -> JSON for profiles/rNN_traffic.json (what bench.py's roofline.traffic reads)"""
+    import json
+    out = {"_comment": "DRAM traffic per launch from `ncu --set full --clock-control none` captures (one launch each); bench.py scales "
+                       "it by cells per launch for roofline.traffic"}
+    for pr in pairs:
+        key, path = pr.split("=", 1)
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(txt.splitlines()))
+        h, u, r = rows[0], rows[1], rows[2]
+
+        def val(name):
+            v, unit = float(r[h.index(name)].replace(",", "")), u[h.index(name)]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        out[key] = {"kernel": short(r[h.index("Kernel Name")]), "cells": cells, "dram_bytes_read": val("dram__bytes_read.sum"),
+                    "dram_bytes_write": val("dram__bytes_write.sum"), "report": path.split("/")[-1]}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "traffic":
+        traffic(int(sys.argv[2]), sys.argv[3:])
     else:
         full(sys.argv[2:])

@@ -17,7 +17,7 @@ import parallelpoissonsolver_b200 as pps  # noqa: E402
 PASSES = {  # vector passes (8 B per cell each) per launch of a kernel class
     "stencil_dot(v=A*p, r0.v)": 3, "s_update(r-=alpha*v)": 3, "stencil_dot2(t=A*s, s.t, t.t)": 2,
     "xr_update(x+=.., r-=omega*t, r0.r, r.r)": 7, "p_update(p=r+beta*(p-omega*v))": 4, "cheb_first": 3, "cheb_step": 4,
-    "residual(r=b-A*x, r.r)": 3, "stencil(y=A*x)": 2, "cg_apply(Ap, r.z, p.Ap)": 3, "cg_xr": 6, "cg_p": 3, "dot": 2,
+    "residual(r=b-A*x, r.r)": 3, "fused_p(p=r+beta*(p-omega*v), v=A*p, r0.v)": 6, "fused_s(s=r-alpha*v, t=A*s, s.t, t.t)": 4, "stencil(y=A*x)": 2, "cg_apply(Ap, r.z, p.Ap)": 3, "cg_xr": 6, "cg_p": 3, "dot": 2,
 }
 
 
@@ -82,10 +82,23 @@ def solve(n, cheb=False, max_iter=4000):
     s.close()
 
 
+def iters(n, k):
+    """K iterations of the bench problem at n^3 (short: for ncu captures)"""
+    X, B = manufactured(n)
+    s = pps.PoissonSolver(pps.make_config((n, n, n), max_iter=k))
+    s.set_fields(0, X, B)
+    s.solve()
+    print(json.dumps(dict(kind="iters", n=n, iters=s.iterations, err=s.error_iteration, loop_s=s.loop_seconds,
+                          kernels=[k_["name"] for k_ in s.kernel_stats()])), flush=True)
+    s.close()
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     n = int(sys.argv[2])
     if what == "stencil":
         stencil_sweep(n)
+    elif what == "iters":
+        iters(n, int(sys.argv[3]))
     else:
         solve(n, cheb=len(sys.argv) > 3 and sys.argv[3] == "cheb")
