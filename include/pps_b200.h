@@ -54,6 +54,13 @@ enum { PPS_FUSE_AUTO = 0,   /* best measured schedule */
        PPS_FUSE_SPLIT = 1,  /* one kernel per reference loop nest group (19 vector passes / BiCGSTAB iteration) */
        PPS_FUSE_FULL = 2    /* axpy updates fused into the operator kernels (17 passes) */ };
 
+/* eigenvalue bounds of the Chebyshev preconditioner: GLOBAL = whole grid, rescaled by cheb_rescale_min/max and (1 + epsilon)
+ * (chebyshevIteration.hpp:22-26); LOCAL = the block's own bounds, not rescaled (alpaka tree, chebyshevIterationAlpaka.hpp:30-31) */
+enum { PPS_CHEB_EIG_GLOBAL = 0, PPS_CHEB_EIG_LOCAL = 1 };
+/* precision of the Chebyshev iterates: FP32 = mixed-precision preconditioner (B is cast to float, the sweeps run in float with
+ * the alpaka tree's folded 7-point form, X = -(float)W widened to double; kernelsAlpakaChebyshev.hpp:8-18,136-183,233-270) */
+enum { PPS_CHEB_FP64 = 0, PPS_CHEB_FP32 = 1 };
+
 typedef struct pps_config {
     int abi_version;          /* PPS_ABI_VERSION */
     int dim;                  /* DIM, inputParam.hpp:16 (3) */
@@ -78,7 +85,13 @@ typedef struct pps_config {
     int flags;                /* PPS_FLAG_* */
     int precond_max_iter;     /* iterMaxPreconditioner, solverSetup.hpp:32 (nested Krylov preconditioners); 0 = 150 */
     double precond_tolerance; /* tollPreconditionerSolver * tollScalingFactor, solverSetup.hpp:31; 0 = 1e4 * 1e-10 */
-    int reserved[4];
+    /* alpaka-only configuration surface; 0 = the CPU tree's behaviour */
+    int cheb_eigenvalues;     /* PPS_CHEB_EIG_*: `global` / `local` of solverPoissonMPI_alpaka/include/inputParam.hpp:21-22,27-29 */
+    int cheb_precision;       /* PPS_CHEB_FP*: T_data_chebyshev of solverPoissonMPI_alpaka/include/solverSetup.hpp:14 */
+    int cheb_block;           /* Chebyshev sweeps advanced per HBM pass by the temporally blocked kernel (0 = one kernel per sweep, 1..4) */
+    int precond_communication; /* communicationON / OFF template argument of the preconditioner (inputParam.hpp:20-21,28): 0 = OFF, block-Jacobi
+                                  (shipped); 1 = ON, the Chebyshev preconditioner exchanges the faces of B and of every iterate
+                                  (chebyshevIteration.hpp:69-73,97-101) -- a global polynomial preconditioner */
 } pps_config;
 
 /* pps_config.flags */

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <string>
 #include <vector>
 
 #include "../pps_b200.h"
@@ -42,9 +43,50 @@ struct StackInfo {
     int inner_iterations = 0;  // maxIteration of the Chebyshev iteration inside a nested CG (T_Preconditioner3, inputParam.hpp:29)
 };
 
+// TimeCounter of the alpaka tree (solverPoissonMPI_alpaka/include/solverSetup.hpp:207-286), printed by its main.cpp:156 as
+// `solver.timeCounter.printAverageTime(solver.getNumIterationFinal())`.  Here the phases are the kernel classes of libpps_b200.so,
+// timed with CUDA events on the launching stream when the solve ran with phase timers on (environment PPS_PHASE_TIMERS=1 or
+// -DPPS_PHASE_TIMERS; two event records per launch, a few per cent of overhead).  The aggregate rows keep the alpaka names.
+class TimeCounterAdapter {
+  public:
+    void attach(pps_handle* h) { h_ = h; }
+    void printAverageTime(const int numCycles) const {
+        if (!h_ || numCycles <= 0) return;
+        double precond = 0, comm = 0, allred = 0, kernels = 0, ghosts = 0, total = 0;
+        std::cout << "Time in milliseconds " << std::endl;
+        for (int k = 0;; k++) {
+            double avg = 0;
+            long long n = 0;
+            const char* name = nullptr;
+            if (pps_get_kernel_stats(h_, k, &avg, &n, &name)) break;
+            if (n == 0) continue;
+            const double per_cycle = avg * static_cast<double>(n) / numCycles;
+            const std::string nm(name);
+            std::cout << "timeTot[" << nm << "] " << per_cycle << "  (" << static_cast<double>(n) / numCycles << " launches per cycle)" << std::endl;
+            if (nm.rfind("cheb", 0) == 0) precond += per_cycle;
+            else if (nm == "halo") comm += per_cycle;
+            else if (nm == "scalar_op") allred += per_cycle;
+            else if (nm == "neumann_ghost") ghosts += per_cycle;
+            else if (nm != "setup" && nm.rfind("residual", 0) != 0) kernels += per_cycle;
+            total += per_cycle;
+        }
+        std::cout << "timeTotPreconditionerTot " << precond << std::endl;
+        std::cout << "timeTotCommunicationTot " << comm << std::endl;
+        std::cout << "timeTotAllReductionTot " << allred << std::endl;
+        std::cout << "timeTotKernelsBBiCGstabTot " << kernels << std::endl;
+        std::cout << "timeTotResetNeumanBCs " << ghosts << std::endl;
+        std::cout << "timeTotal " << total << std::endl;
+    }
+
+  private:
+    pps_handle* h_ = nullptr;
+};
+
 template <int DIM, typename T_data, int maxIteration>
 class SolverAdapter {
   public:
+    TimeCounterAdapter timeCounter;   // alpaka tree: iterativeSolverBaseAlpaka.hpp:640
+
     SolverAdapter(const BlockGrid<DIM, T_data>& blockGrid, const ExactSolutionAndBCs<DIM, T_data>& exact,
                   CommunicatorMPI<DIM, T_data>&, const StackInfo& self, const StackInfo& precond, int tolerance, const char* name)
         : grid_(blockGrid), exact_(exact), name_(name), rank_(blockGrid.getMyrank()) {
@@ -61,10 +103,7 @@ class SolverAdapter {
             std::cerr << "Error: ChebyshevIteration as main solver ignores its preconditioner slot: use NoneSolver there" << std::endl;
             std::exit(-1);
         }
-        if (precond.precond_kind == PPS_PRECOND_CHEBYSHEV && precond.communication) {
-            std::cerr << "Error: the Chebyshev preconditioner is implemented with communicationOFF (block-Jacobi) only" << std::endl;
-            std::exit(-1);
-        }
+
         pps_config c;
         pps_default_config(&c);
         c.dim = DIM;
@@ -92,6 +131,17 @@ class SolverAdapter {
         c.cheb_rescale_min = rescaleEigMin;
         c.cheb_rescale_max = rescaleEigMax;
         c.order_neumann = orderNeumanBcs;
+        // communicationON in the preconditioner slot: the Chebyshev sweeps exchange faces (chebyshevIteration.hpp:69-73,97-101)
+        c.precond_communication = (precond.precond_kind == PPS_PRECOND_CHEBYSHEV && precond.communication) ? 1 : 0;
+        // alpaka-only switches, for a solverSetup.hpp / inputParam.hpp written for that tree:
+        //   -DPPS_CHEBYSHEV_FLOAT       T_data_chebyshev = float   (solverPoissonMPI_alpaka/include/solverSetup.hpp:14)
+        //   -DPPS_CHEBYSHEV_LOCAL_EIG   `local` eigenvalue bounds  (solverPoissonMPI_alpaka/include/inputParam.hpp:21-22,27)
+#ifdef PPS_CHEBYSHEV_FLOAT
+        c.cheb_precision = PPS_CHEB_FP32;
+#endif
+#ifdef PPS_CHEBYSHEV_LOCAL_EIG
+        c.cheb_eigenvalues = PPS_CHEB_EIG_LOCAL;
+#endif
         if (const char* a = std::getenv("PPS_ARITHMETIC")) c.arithmetic = std::atoi(a);
         cfg_ = c;
         precondIterations_ = precond.precond_kind == PPS_PRECOND_CHEBYSHEV ? precond.iterations : 0;
@@ -165,6 +215,13 @@ class SolverAdapter {
             if (pps_set_neumann_face(h_, rank_, face, g.data(), g.size())) die("pps_set_neumann_face");
         }
         if (shared_) barrier();
+        timeCounter.attach(h_);
+#ifdef PPS_PHASE_TIMERS
+        const bool phase_timers = true;
+#else
+        const bool phase_timers = std::getenv("PPS_PHASE_TIMERS") != nullptr && std::atoi(std::getenv("PPS_PHASE_TIMERS")) != 0;
+#endif
+        if (phase_timers && (!shared_ || rank_ == 0)) pps_set_profiling(h_, 1);
         if (!shared_ || rank_ == 0)
             if (pps_solve(h_)) die("pps_solve");
         if (shared_) barrier();

@@ -42,6 +42,9 @@ SOLVER_TYPEDEFS = {
     # Chebyshev inside of inputParam.hpp:29 in the preconditioner slot
     "bicgstab_bicgloc": "BiCGSTAB<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, T_Preconditioner>",
     "bicgstab_cgcheb": "BiCGSTAB<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, T_Preconditioner3>",
+    # GLOBAL Chebyshev preconditioner: the same class with communicationON in the preconditioner slot (chebyshevIteration.hpp:69-73,97-101)
+    "bicgstab_chebglobal": "BiCGSTAB<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, "
+                           "ChebyshevIteration<DIM, T_data, tollPreconditionerSolver, chebyshevMax, ischebyshevMainLoop, communicationON, T_NoneSolver>>",
     # Chebyshev iteration as the MAIN solver (chebyshevIteration.hpp:61-67,132-139): isMainLoop = true, communicationON
     "cheb_main": "ChebyshevIteration<DIM, T_data, tollMainSolver, chebyshevMax, true, communicationON, T_NoneSolver>",
 }
@@ -91,6 +94,8 @@ CONFIGS = {
     "l48": cfg((48, 1, 1), MIXED, "bicgstab_none", ds=(0.05, 0.1, 0.1), origin=(0.3, -0.2, 0.1), dim=1),
     "l48_cheb": cfg((48, 1, 1), (1, 0, 0, 0, 0, 0), "bicgstab_cheb", ds=(0.05, 0.1, 0.1), origin=(0.3, -0.2, 0.1), dim=1),
     "d128": cfg((128, 128, 128)),
+    "d32_chebg": cfg((32, 32, 32), solver="bicgstab_chebglobal"),
+    "m24_chebg": cfg((24, 20, 28), MIXED, "bicgstab_chebglobal", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1)),
     # CPU-baseline samples for bench.py --impl reference (bounded: fixed iteration count)
     "bench256": cfg((256, 256, 256), iter_max=10000),
     "bench512_it8": cfg((512, 512, 512), iter_max=8),

@@ -24,6 +24,7 @@ typedef struct {
     double *p, *r, *r0, *Mp, *AMp, *z, *Az; /* BiCGSTAB.hpp:23-29 ; CG uses p, r, AMp(=Apk), z */
     double *cy, *cz, *cw;                   /* chebyshevIteration.hpp:28-30 */
     double *lw[7];                          /* work arrays of a nested (local) Krylov preconditioner: p r r0 Mp AMp z Az */
+    double theta, delta, sigma;             /* Chebyshev constants of the preconditioner on this block (global, or the block's own) */
 } Block;
 
 struct orc {
@@ -63,6 +64,9 @@ void orc_default_config(orc_config* c) {
     c->precond_max_iter = 150;
     c->order_neumann = 2;
     c->dim = 3;
+    c->cheb_eig_local = 0;
+    c->cheb_f32 = 0;
+    c->precond_comm = 0;
 }
 
 /* ---------------------------------------------------------------- geometry (blockGrid.hpp) */
@@ -142,6 +146,17 @@ orc_t* orc_create(const orc_config* c) {
     o->theta = (eg[0] * c->cheb_rescale_min + eg[1] * c->cheb_rescale_max) * 0.5 * (1.0 + c->cheb_epsilon);
     o->delta = (eg[0] * c->cheb_rescale_min - eg[1] * c->cheb_rescale_max) * 0.5;
     o->sigma = o->theta / o->delta;
+    for (int r = 0; r < o->world; r++) {
+        Block* B = &o->blk[r];
+        B->theta = o->theta; B->delta = o->delta;
+        if (c->cheb_eig_local) {
+            /* alpaka tree, `local` (chebyshevIterationAlpaka.hpp:30-31,71-76): (l0 + l1) / 2 and (l1 - l0) / 2 of the rank's own block,
+             * no rescaling, no epsilon; delta keeps the CPU tree's sign here (the alpaka sign is applied where its kernels are restated) */
+            B->theta = (B->eig_local[0] + B->eig_local[1]) * 0.5;
+            B->delta = (B->eig_local[0] - B->eig_local[1]) * 0.5;
+        }
+        B->sigma = B->theta / B->delta;
+    }
     const long nh = (long)(c->max_iter > c->cheb_max ? c->max_iter : c->cheb_max) + 2;
     o->hist = zalloc(nh); o->h_alpha = zalloc(nh); o->h_omega = zalloc(nh); o->h_rho = zalloc(nh);
     o->norm_b = 1.0;
@@ -415,7 +430,7 @@ static double residual_norm(orc_t* o, double norm_b) {
 static void chebyshev_block(orc_t* o, int rank, double* X, double* Bf) {
     /* chebyshevIteration.hpp:48-140 with isMainLoop = false, communicationON = false */
     Block* B = &o->blk[rank];
-    const double theta = o->theta, delta = o->delta, sigma = o->sigma;
+    const double theta = B->theta, delta = B->delta, sigma = B->sigma;
     double rhoOld = 1 / sigma;
     double rhoCurr = 1 / (2 * sigma - rhoOld);
     orc_reset_neumann(o, rank, Bf, 0, 1.0);
@@ -436,6 +451,75 @@ static void chebyshev_block(orc_t* o, int rank, double* X, double* Bf) {
         t = B->cw; B->cw = B->cy; B->cy = t;           /* swap(fieldW, fieldY) */
     }
     FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; X[q] = (-1) * B->cw[q]; }
+}
+
+/* Mixed-precision Chebyshev preconditioner of the alpaka tree (T_data_chebyshev = float), communicationOFF:
+ * chebyshevIterationAlpaka.hpp:116-310 (host loop, `cast` branch :149-190, X = -W :293-294) with the kernels
+ * CastPrecisionFieldKernel (kernelsAlpakaChebyshev.hpp:8-18), Chebyshev1Kernel (:136-183), Chebyshev2Kernel (:233-270) and
+ * AssignFieldWith1FieldKernel (:24-45).  RESTATEMENT ONLY: the alpaka tree cannot be built in this image (alpaka, Boost, MPI),
+ * so nothing pins these lines to a run of the reference -- parity unpinned.  Every operation is a float operation in the
+ * kernels' own order, no contraction (this file is compiled with -ffp-contract=off).
+ * The alpaka tree's delta has the opposite sign of the CPU tree's (chebyshevIterationAlpaka.hpp:29), hence -B->delta. */
+static void chebyshev_block_alpaka_f32(orc_t* o, int rank, double* X, double* Bf) {
+    Block* B = &o->blk[rank];
+    const float theta = (float)B->theta, delta = (float)(-B->delta), sigma = (float)(B->theta / -B->delta);   /* :28-33,67-69,597-599 */
+    float rhoOld = 1 / sigma;                                                                                  /* :123 */
+    float rhoCurr = 1 / (2 * sigma - rhoOld);                                                                  /* :124 */
+    orc_reset_neumann(o, rank, Bf, 0, 1.0);                                                                    /* :127, on the fp64 field */
+    float* bt = (float*)calloc((size_t)B->ntot, sizeof(float));
+    float* y = (float*)calloc((size_t)B->ntot, sizeof(float));
+    float* z = (float*)calloc((size_t)B->ntot, sizeof(float));
+    float* w = (float*)calloc((size_t)B->ntot, sizeof(float));
+    for (long q = 0; q < B->ntot; q++) bt[q] = (float)Bf[q];                                                   /* CastPrecisionFieldKernel */
+    /* alpaka vectors are ordered Z Y X: ds[2] of the kernels is dx */
+    const float r0 = (float)(o->c.ds[0] * o->c.ds[0]), r1 = (float)(o->c.ds[1] * o->c.ds[1]), r2 = (float)(o->c.ds[2] * o->c.ds[2]);
+    const long sj = B->sj, sk = B->sk;
+    {
+        const float f0 = 2 * rhoCurr / delta * (1 / r0 / theta);                                               /* :148-150 */
+        const float f1 = 2 * rhoCurr / delta * (1 / r1 / theta);
+        const float f2 = 2 * rhoCurr / delta * (1 / r2 / theta);
+        const float fc0 = 2 * rhoCurr / delta * (2 - 2 * (1 / r0 + 1 / r1 + 1 / r2) / theta);                   /* :159 */
+        FOR_SOLVER(B, i, j, k) {
+            const long q = i + sj * j + sk * k;
+            z[q] = bt[q] / theta;                                                                              /* :155 */
+            float tmp = bt[q] * fc0 + (bt[q - 1] + bt[q + 1]) * f0;                                            /* :161 */
+            tmp += (bt[q - sj] + bt[q + sj]) * f1 + (bt[q - sk] + bt[q + sk]) * f2;                            /* :162-163 */
+            y[q] = tmp;
+        }
+    }
+    for (int c = 2; c <= o->c.cheb_max; c++) {                                                                 /* :156-190 */
+        rhoOld = rhoCurr;
+        rhoCurr = 1 / (2 * sigma - rhoOld);
+        /* resetNeumanBCsAlpakaCast<float, false, false>(bufY): plain mirrors on the float field (iterativeSolverBaseAlpaka.hpp:145-186) */
+        for (int f = 0; f < 6; f++) {
+            if (!(B->hb[f] && o->c.bcs[f] == 1)) continue;
+            const int d = f / 2, up = f % 2;
+            const int u = d == 0 ? 1 : 0, v = d == 2 ? 1 : 2;
+            const long sd = d == 0 ? 1 : (d == 1 ? sj : sk), su = u == 0 ? 1 : sj, sv = v == 1 ? sj : sk;
+            const int ghost = up ? B->n[d] + 1 : 0;
+            const int src = o->c.order_neumann == 1 ? (up ? B->n[d] : 1) : (up ? B->n[d] - 1 : 2);
+            for (int b2 = 1; b2 <= B->n[v]; b2++)
+                for (int a2 = 1; a2 <= B->n[u]; a2++) y[ghost * sd + a2 * su + b2 * sv] = y[src * sd + a2 * su + b2 * sv];
+        }
+        const float f0 = rhoCurr * 2 / delta * (1 / r0);                                                       /* :240-246 */
+        const float f1 = rhoCurr * 2 / delta * (1 / r1);
+        const float f2 = rhoCurr * 2 / delta * (1 / r2);
+        const float fB = rhoCurr * 2 / delta;
+        const float fZ = -rhoCurr * rhoOld;
+        const float fc0 = rhoCurr * (2 * sigma - 4 / delta * (1 / r0 + 1 / r1 + 1 / r2));                      /* :255 */
+        FOR_SOLVER(B, i, j, k) {
+            const long q = i + sj * j + sk * k;
+            float tmp = y[q] * fc0 + (y[q - 1] + y[q + 1]) * f0;                                               /* :257 */
+            tmp += (y[q - sj] + y[q + sj]) * f1 + (y[q - sk] + y[q + sk]) * f2;                                /* :258 */
+            tmp += bt[q] * fB;                                                                                 /* :267 */
+            tmp += z[q] * fZ;                                                                                  /* :268 */
+            w[q] = tmp;
+        }
+        float* t = z; z = y; y = t;   /* swap(bufZ, bufY)  :184-185 */
+        t = w; w = y; y = t;          /* swap(bufW, bufY)  :186-187 */
+    }
+    FOR_SOLVER(B, i, j, k) { const long q = i + sj * j + sk * k; X[q] = (double)((float)(-1.0) * w[q]); }     /* :293-294 */
+    free(bt); free(y); free(z); free(w);
 }
 
 /* ---- nested Krylov preconditioners: isMainLoop = false, communicationON = false -> everything is rank-local.
@@ -548,9 +632,51 @@ static void local_cg_chebyshev(orc_t* o, int rank, double* X, double* Bf) {
     for (long q = 0; q < B->ntot; q++) { X[q] *= nrm; Bf[q] *= nrm; }
 }
 
-void orc_precondition(orc_t* o, double* const* X, double* const* Bf) {
+/* ChebyshevIteration<..., isMainLoop = false, communicationON = true, ...> in the preconditioner slot (chebyshevIteration.hpp:48-140):
+ * every rank exchanges the faces of B (:69-73) and of every iterate Y (:97-101) before the sweep -- all ranks in lock-step */
+static void chebyshev_all_comm(orc_t* o, double* const* X, double* const* Bf) {
+    const double theta = o->theta, delta = o->delta, sigma = o->sigma;
+    double rhoOld = 1 / sigma;
+    double rhoCurr = 1 / (2 * sigma - rhoOld);
+    double** ys = (double**)malloc(sizeof(double*) * (size_t)o->world);
+    orc_halo_exchange(o, (double* const*)Bf);
     for (int r = 0; r < o->world; r++) {
-        if (o->c.precond == ORC_PRECOND_CHEBYSHEV) chebyshev_block(o, r, X[r], Bf[r]);
+        Block* B = &o->blk[r];
+        orc_reset_neumann(o, r, Bf[r], 0, 1.0);
+        FOR_SOLVER(B, i, j, k) {
+            const long q = i + B->sj * j + B->sk * k;
+            B->cz[q] = Bf[r][q] / theta;
+            B->cy[q] = 2 * rhoCurr / delta * (2 * Bf[r][q] + stencil(o, B, Bf[r], i, j, k) / theta);
+        }
+    }
+    for (int c = 2; c <= o->c.cheb_max; c++) {
+        rhoOld = rhoCurr;
+        rhoCurr = 1 / (2 * sigma - rhoOld);
+        for (int r = 0; r < o->world; r++) ys[r] = o->blk[r].cy;
+        orc_halo_exchange(o, ys);
+        for (int r = 0; r < o->world; r++) {
+            Block* B = &o->blk[r];
+            orc_reset_neumann(o, r, B->cy, 0, 1.0);
+            FOR_SOLVER(B, i, j, k) {
+                const long q = i + B->sj * j + B->sk * k;
+                B->cw[q] = rhoCurr * (2 * sigma * B->cy[q] + 2 / delta * (Bf[r][q] + stencil(o, B, B->cy, i, j, k)) - rhoOld * B->cz[q]);
+            }
+            double* t = B->cz; B->cz = B->cy; B->cy = t;
+            t = B->cw; B->cw = B->cy; B->cy = t;
+        }
+    }
+    for (int r = 0; r < o->world; r++) {
+        Block* B = &o->blk[r];
+        FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; X[r][q] = (-1) * B->cw[q]; }
+    }
+    free(ys);
+}
+
+void orc_precondition(orc_t* o, double* const* X, double* const* Bf) {
+    if (o->c.precond == ORC_PRECOND_CHEBYSHEV && o->c.precond_comm && !o->c.cheb_f32) { chebyshev_all_comm(o, X, Bf); return; }
+    for (int r = 0; r < o->world; r++) {
+        if (o->c.precond == ORC_PRECOND_CHEBYSHEV && o->c.cheb_f32) chebyshev_block_alpaka_f32(o, r, X[r], Bf[r]);
+        else if (o->c.precond == ORC_PRECOND_CHEBYSHEV) chebyshev_block(o, r, X[r], Bf[r]);
         else if (o->c.precond == ORC_PRECOND_BICGSTAB_LOCAL) local_bicgstab(o, r, X[r], Bf[r]);
         else if (o->c.precond == ORC_PRECOND_CG_CHEB_LOCAL) local_cg_chebyshev(o, r, X[r], Bf[r]);
         else memcpy(X[r], Bf[r], sizeof(double) * (size_t)o->blk[r].ntot);   /* noneSolver.hpp:24-27 */

@@ -45,6 +45,12 @@ typedef struct orc_config {
     int precond_max_iter;     /* iterMaxPreconditioner   solverSetup.hpp:32 */
     int order_neumann;        /* orderNeumanBcs: 2 (shipped) or 1   solverSetup.hpp:25 */
     int dim;                  /* DIM: 3 (shipped), 2 or 1   inputParam.hpp:16; axes >= dim hold one point, no guards (blockGrid.hpp:160-206) */
+    /* alpaka-only configuration surface (solverPoissonMPI_alpaka; that tree needs alpaka + Boost + MPI and cannot be built here, so
+     * these two are a RESTATEMENT ONLY -- parity unpinned, see the functions that use them) */
+    int cheb_eig_local;       /* 1: `local` of solverPoissonMPI_alpaka/include/inputParam.hpp:21-22: block-local, not rescaled eigenvalue bounds */
+    int cheb_f32;             /* 1: T_data_chebyshev = float, solverPoissonMPI_alpaka/include/solverSetup.hpp:14 (mixed-precision preconditioner) */
+    int precond_comm;         /* 1: the Chebyshev preconditioner runs with communicationON (face exchange of B and of every iterate,
+                                 chebyshevIteration.hpp:69-73,97-101) -- a GLOBAL polynomial preconditioner instead of block-Jacobi */
 } orc_config;
 
 typedef struct orc_block_info {

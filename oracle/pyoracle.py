@@ -25,6 +25,7 @@ class OrcConfig(C.Structure):
         ("max_iter", C.c_int), ("cheb_max", C.c_int), ("cheb_epsilon", C.c_double),
         ("cheb_rescale_min", C.c_double), ("cheb_rescale_max", C.c_double),
         ("precond_tolerance", C.c_double), ("precond_max_iter", C.c_int), ("order_neumann", C.c_int), ("dim", C.c_int),
+        ("cheb_eig_local", C.c_int), ("cheb_f32", C.c_int), ("precond_comm", C.c_int),
     ]
 
 
@@ -100,7 +101,8 @@ def _dptr(a: np.ndarray):
 def make_config(np_=(128, 128, 256), nranks=(1, 1, 1), ds=(0.1, 0.1, 0.1), origin=(0.0, 0.0, 0.0),
                 bcs=(0, 1, 0, 1, 0, 1), solver=SOLVER_BICGSTAB, precond=PRECOND_NONE, tolerance=1e-8,
                 max_iter=1700, cheb_max=11, cheb_epsilon=1e-4, cheb_rescale_min=500.0,
-                cheb_rescale_max=1 - 1e-4, precond_tolerance=1e4 * 1e-10, precond_max_iter=150, order_neumann=2, dim=3) -> OrcConfig:
+                cheb_rescale_max=1 - 1e-4, precond_tolerance=1e4 * 1e-10, precond_max_iter=150, order_neumann=2, dim=3,
+                cheb_eig_local=0, cheb_f32=0, precond_comm=0) -> OrcConfig:
     c = OrcConfig()
     c.np[:] = list(np_)
     c.nranks[:] = list(nranks)
@@ -113,6 +115,7 @@ def make_config(np_=(128, 128, 256), nranks=(1, 1, 1), ds=(0.1, 0.1, 0.1), origi
     c.precond_tolerance, c.precond_max_iter = precond_tolerance, precond_max_iter
     c.order_neumann = order_neumann
     c.dim = dim
+    c.cheb_eig_local, c.cheb_f32, c.precond_comm = int(cheb_eig_local), int(cheb_f32), int(precond_comm)
     return c
 
 

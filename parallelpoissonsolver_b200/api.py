@@ -11,6 +11,8 @@ SOLVER_BICGSTAB, SOLVER_CG, SOLVER_CHEBYSHEV = 0, 1, 2
 PRECOND_NONE, PRECOND_CHEBYSHEV, PRECOND_BICGSTAB_LOCAL, PRECOND_CG_CHEB_LOCAL = 0, 1, 2, 3
 ARITH_FAST, ARITH_PARITY = 0, 1
 FUSE_AUTO, FUSE_SPLIT, FUSE_FULL = 0, 1, 2
+CHEB_EIG_GLOBAL, CHEB_EIG_LOCAL = 0, 1      # alpaka tree inputParam.hpp:21-22 (`global` / `local`)
+CHEB_FP64, CHEB_FP32 = 0, 1                 # alpaka tree solverSetup.hpp:14 (T_data_chebyshev)
 FLAG_OPERATOR_ONLY = 1
 ABI_VERSION = 1
 UNIQUE_ID_BYTES = 128
@@ -30,7 +32,10 @@ class Config(C.Structure):
         ("cheb_max_iter", C.c_int), ("cheb_epsilon", C.c_double), ("cheb_rescale_min", C.c_double),
         ("cheb_rescale_max", C.c_double), ("order_neumann", C.c_int), ("arithmetic", C.c_int), ("fusion", C.c_int),
         ("device", C.c_int), ("flags", C.c_int), ("precond_max_iter", C.c_int), ("precond_tolerance", C.c_double),
-        ("reserved", C.c_int * 4),
+        ("cheb_eigenvalues", C.c_int),
+        ("cheb_precision", C.c_int),
+        ("cheb_block", C.c_int),
+        ("precond_communication", C.c_int),
     ]
 
 
@@ -113,7 +118,8 @@ def default_config() -> Config:
 def make_config(npglobal, nranks=(1, 1, 1), ds=(0.1, 0.1, 0.1), origin=(0.0, 0.0, 0.0), bcs=(0, 0, 0, 0, 0, 0),
                 solver=SOLVER_BICGSTAB, precond=PRECOND_NONE, tolerance=1e-8, max_iter=1700, cheb_max_iter=11,
                 cheb_epsilon=1e-4, cheb_rescale_min=500.0, cheb_rescale_max=1 - 1e-4, arithmetic=ARITH_FAST,
-                fusion=FUSE_AUTO, device=-1, flags=0, order_neumann=2, precond_tolerance=1e4 * 1e-10, precond_max_iter=150, dim=3) -> Config:
+                fusion=FUSE_AUTO, device=-1, flags=0, order_neumann=2, precond_tolerance=1e4 * 1e-10, precond_max_iter=150, dim=3,
+                cheb_eigenvalues=CHEB_EIG_GLOBAL, cheb_precision=CHEB_FP64, cheb_block=0, precond_communication=0) -> Config:
     c = Config()
     c.abi_version = ABI_VERSION
     c.dim = int(dim)
@@ -131,6 +137,8 @@ def make_config(npglobal, nranks=(1, 1, 1), ds=(0.1, 0.1, 0.1), origin=(0.0, 0.0
     c.precond_tolerance, c.precond_max_iter = float(precond_tolerance), int(precond_max_iter)
     c.arithmetic, c.fusion, c.device = arithmetic, fusion, device
     c.flags = flags
+    c.cheb_eigenvalues, c.cheb_precision, c.cheb_block = int(cheb_eigenvalues), int(cheb_precision), int(cheb_block)
+    c.precond_communication = int(precond_communication)
     return c
 
 

@@ -40,7 +40,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not _newer(LIB, deps):
         return LIB
     cus = sorted(s for s in deps if s.endswith(".cu"))
-    cmd = [NVCC] + ARCH + NVCC_FLAGS + ["-shared", "-cudart", "static", "-o", LIB] + cus + ["-ldl"]
+    cmd = [NVCC] + ARCH + NVCC_FLAGS + ["--threads", "4", "-shared", "-cudart", "static", "-o", LIB] + cus + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -117,7 +117,7 @@ __device__ __forceinline__ void apply_scalar_op(int op, Ctl* c) {
     }
 }
 
-__global__ void scalar_op_kernel(int op, Ctl* c, int ignore_done) {
+static __global__ void scalar_op_kernel(int op, Ctl* c, int ignore_done) {
     if (!ignore_done && c->done) return;
     apply_scalar_op(op, c);
 }
@@ -608,7 +608,7 @@ struct OpCgP {
 // whole-array kernels (guards and padding included, like the reference's 0..ntot loops)
 // ------------------------------------------------------------------------------------------------
 // mode 0: a /= norm_b (iterativeSolverBase.hpp:227-231)   mode 1: a *= norm_b (BiCGSTAB.hpp:310-314)
-__global__ void scale_kernel(double* __restrict__ a, double* __restrict__ b, long long n, const Ctl* ctl, int mode,
+static __global__ void scale_kernel(double* __restrict__ a, double* __restrict__ b, long long n, const Ctl* ctl, int mode,
                              int ignore_done) {
     if (!ignore_done && ctl->done) return;
     const double s = ctl->norm_b;
@@ -627,7 +627,7 @@ __global__ void scale_kernel(double* __restrict__ a, double* __restrict__ b, lon
 // ---- nested (block-local) Krylov preconditioners: BiCGSTAB / BaseCG with isMainLoop = false, communicationOFF ----
 // start values of a nested solve (BiCGSTAB.hpp:60-66,127; baseCG.hpp:49-66).  When the OUTER solve has already converged the
 // nested solve starts `done`, so every kernel of it returns at once, and entry 0 of its history tells the host to stop.
-__global__ void inner_begin_kernel(Ctl* c, const Ctl* outer, double tol, int max_iter) {
+static __global__ void inner_begin_kernel(Ctl* c, const Ctl* outer, double tol, int max_iter) {
     c->rho0 = 1; c->alpha = 1; c->omega = 1; c->beta = 1; c->err = -1; c->rz = 1; c->norm_b = 1; c->tol = tol;
     for (int q = 0; q < 8; q++) c->sums[q] = 0;
     c->iter = 0; c->max_iter = max_iter; c->pad = 0;
@@ -636,7 +636,7 @@ __global__ void inner_begin_kernel(Ctl* c, const Ctl* outer, double tol, int max
 }
 // a, b /= (mode 0) or *= (mode 1) the norm the NESTED solve normalised with, over every entry (iterativeSolverBase.hpp:227-231,
 // BiCGSTAB.hpp:310-314); skipped when the OUTER solve is done.  a may be null.
-__global__ void inner_scale_kernel(double* __restrict__ a, double* __restrict__ b, long long n, const Ctl* inner, const Ctl* outer,
+static __global__ void inner_scale_kernel(double* __restrict__ a, double* __restrict__ b, long long n, const Ctl* inner, const Ctl* outer,
                                    int mode) {
     if (outer != nullptr && outer->done) return;
     const double s = inner->norm_b;
@@ -667,7 +667,7 @@ struct FaceGeom {
 //   ghost(A) = mirror(B)                                  helper fields
 //   ghost(A) = mirror(B) -/+ 2 ds dudn / norm_b           solution field in the main loop (:100, :148)
 // orderNeumanBcs == 1 (:92-95, :105-108, :140-143, :153-156): the host passes the boundary plane as B and ds as `two_ds`
-__global__ void neumann_ghost_kernel(double* __restrict__ f, FaceGeom g, const double* __restrict__ dudn, double two_ds,
+static __global__ void neumann_ghost_kernel(double* __restrict__ f, FaceGeom g, const double* __restrict__ dudn, double two_ds,
                                      int upper, const Ctl* ctl, int ignore_done) {
     if (!ignore_done && ctl != nullptr && ctl->done) return;
     const long long n = static_cast<long long>(g.nu) * g.nv;
@@ -692,7 +692,7 @@ struct GhostBatch {
     int upper[6];
     int count;
 };
-__global__ void neumann_ghost_batch_kernel(double* __restrict__ f, GhostBatch batch, const Ctl* ctl, int ignore_done) {
+static __global__ void neumann_ghost_batch_kernel(double* __restrict__ f, GhostBatch batch, const Ctl* ctl, int ignore_done) {
     if (!ignore_done && ctl != nullptr && ctl->done) return;
     const int q = blockIdx.y;
     if (q >= batch.count) return;
@@ -715,7 +715,7 @@ __global__ void neumann_ghost_batch_kernel(double* __restrict__ f, GhostBatch ba
 //   Dirichlet: b(A = first interior plane) -= x(B = boundary plane) / ds^2        (:454, :502)
 //   Neumann:   b(A = boundary plane)      +/-= nfac dudn / ds                      (:475-480, :522-527)
 //              nfac = 2 for orderNeumanBcs == 2, 1 for orderNeumanBcs == 1 (1 * dudn is exact, so both are the reference's bits)
-__global__ void adjust_b_kernel(double* __restrict__ b, const double* __restrict__ x, FaceGeom g,
+static __global__ void adjust_b_kernel(double* __restrict__ b, const double* __restrict__ x, FaceGeom g,
                                 const double* __restrict__ dudn, double ds, int neumann, int upper, double nfac) {
     const long long n = static_cast<long long>(g.nu) * g.nv;
     for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < n;
@@ -732,7 +732,7 @@ __global__ void adjust_b_kernel(double* __restrict__ b, const double* __restrict
 
 // halo between two blocks that live on the same GPU: guard plane (A of dst) <- boundary data plane (B of src)
 // (what CommunicatorMPI::operator() moves per face, communicationMPI.hpp:51-292)
-__global__ void face_copy_kernel(double* __restrict__ dst, const double* __restrict__ src, FaceGeom g, const Ctl* ctl,
+static __global__ void face_copy_kernel(double* __restrict__ dst, const double* __restrict__ src, FaceGeom g, const Ctl* ctl,
                                  int ignore_done) {
     if (!ignore_done && ctl != nullptr && ctl->done) return;
     const long long n = static_cast<long long>(g.nu) * g.nv;
@@ -744,7 +744,7 @@ __global__ void face_copy_kernel(double* __restrict__ dst, const double* __restr
 }
 
 // peer-memory halo path: await the epoch a neighbour's copy engine writes into my flag after its plane has landed
-__global__ void await_epoch_sys_kernel(const unsigned int* flag, unsigned int epoch) {
+static __global__ void await_epoch_sys_kernel(const unsigned int* flag, unsigned int epoch) {
     unsigned int v;
     do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
@@ -754,7 +754,7 @@ __global__ void await_epoch_sys_kernel(const unsigned int* flag, unsigned int ep
 }
 
 // pack / unpack a face into / from a contiguous buffer (NCCL send/recv of x- and y-faces)
-__global__ void face_pack_kernel(double* __restrict__ buf, const double* __restrict__ f, FaceGeom g, const Ctl* ctl,
+static __global__ void face_pack_kernel(double* __restrict__ buf, const double* __restrict__ f, FaceGeom g, const Ctl* ctl,
                                  int ignore_done) {
     if (!ignore_done && ctl != nullptr && ctl->done) return;
     const long long n = static_cast<long long>(g.nu) * g.nv;
@@ -762,7 +762,7 @@ __global__ void face_pack_kernel(double* __restrict__ buf, const double* __restr
          t += static_cast<long long>(gridDim.x) * blockDim.x)
         buf[t] = f[g.base_b + (t % g.nu) * g.stride_u + (t / g.nu) * g.stride_v];
 }
-__global__ void face_unpack_kernel(double* __restrict__ f, const double* __restrict__ buf, FaceGeom g, const Ctl* ctl,
+static __global__ void face_unpack_kernel(double* __restrict__ f, const double* __restrict__ buf, FaceGeom g, const Ctl* ctl,
                                    int ignore_done) {
     if (!ignore_done && ctl != nullptr && ctl->done) return;
     const long long n = static_cast<long long>(g.nu) * g.nv;

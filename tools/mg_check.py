@@ -61,6 +61,8 @@ def main():
         s.solve()
         return s, s.get_solution(rank)
 
+    if "fusecmp" in flags:
+        os.environ["PPS_ZCHUNK_STENCIL"] = "8"   # one reduction tree for both schedules (the default picks z-chunks per kernel)
     s, x = solve_with(pps.FUSE_AUTO)
     fused_equals_split = None
     if "fusecmp" in flags:
