@@ -98,6 +98,9 @@ typedef struct pps_config {
 #define PPS_FLAG_OPERATOR_ONLY 1   /* allocate only what pps_bench_operator / pps_apply_operator need (3 vectors instead of 7+):
                                       the operator-apply bandwidth sweep up to the largest grid that fits the GPU; pps_solve fails */
 
+#define PPS_FLAG_NO_DOT_VECTOR 2    /* with PPS_FLAG_OPERATOR_ONLY: 2 vectors only (x, y): pps_bench_operator without the fused dot, for the
+                                      largest grid that fits (2 x 8 B x 2176^3 = 165 GB) */
+
 typedef struct pps_block_info {   /* BlockGrid getters, blockGrid.hpp:40-145 */
     int rank;
     int global_location[3];

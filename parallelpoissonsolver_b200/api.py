@@ -14,6 +14,7 @@ FUSE_AUTO, FUSE_SPLIT, FUSE_FULL = 0, 1, 2
 CHEB_EIG_GLOBAL, CHEB_EIG_LOCAL = 0, 1      # alpaka tree inputParam.hpp:21-22 (`global` / `local`)
 CHEB_FP64, CHEB_FP32 = 0, 1                 # alpaka tree solverSetup.hpp:14 (T_data_chebyshev)
 FLAG_OPERATOR_ONLY = 1
+FLAG_NO_DOT_VECTOR = 2
 ABI_VERSION = 1
 UNIQUE_ID_BYTES = 128
 

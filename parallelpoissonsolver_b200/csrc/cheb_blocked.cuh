@@ -137,7 +137,17 @@ struct ChebIO {
 
 // ------------------------------------------------------------------------------------------------
 // the kernel: grid = x tiles * y tiles * z chunks, block = 32 x FY
+//
+// The kernel is instruction-issue bound, not bandwidth bound (ncu / SASS of the first version: ~700 instructions per march
+// step for 84 fp64 operations), so the march is written for a short instruction stream:
+//   * the three-plane register windows ROTATE instead of shifting: the march is unrolled by three and step R writes the new
+//     plane into slot R (new = w[R], mid = w[R+2 mod 3], old = w[R+1 mod 3]) -- no register moves;
+//   * loads are two predicated 8-byte loads per field (no divergent branches, no zero-filling), the plane test is CTA-uniform;
+//   * the Neumann remaps in x / y exist only in the instantiation that boundary CTAs take (CTA-uniform branch); the z remap is
+//     a step-uniform branch.
 // ------------------------------------------------------------------------------------------------
+template <int N> struct ChebInt { static constexpr int value = N; };
+
 template <int NLEV, int FY, bool FIRST, bool LAST, class Form>
 __global__ void __launch_bounds__(32 * FY) cheb_blocked_kernel(Dims d, Box rg, ChebTile tl, Form fm, ChebIO<typename Form::T> io,
                                                               const Ctl* ctl) {
@@ -161,38 +171,36 @@ __global__ void __launch_bounds__(32 * FY) cheb_blocked_kernel(Dims d, Box rg, C
     const bool o1 = a1 && jo && i0 + 1 >= ox && i0 + 1 < ox + tl.wx;
     // offset of (i0, j) inside a plane; only dereferenced where a0 / a1 hold, i.e. inside the array
     const long long rowoff = static_cast<long long>(kOff) + i0 + d.pitch * static_cast<long long>(max(0, min(j, d.ny + 1)));
-    // Neumann remaps (ghost value = opposite neighbour for order 2, centre for order 1)
-    const int xl0 = (i0 == 1) ? tl.nm[0] : 0, xh0 = (i0 == d.nx) ? tl.nm[1] : 0;
-    const int xl1 = (i0 + 1 == 1) ? tl.nm[0] : 0, xh1 = (i0 + 1 == d.nx) ? tl.nm[1] : 0;
-    const int yl = (j == 1) ? tl.nm[2] : 0, yh = (j == d.ny) ? tl.nm[3] : 0;
     const int rm = max(row - 1, 0), rp = min(row + 1, FY - 1);
+    const T* __restrict__ pF = FIRST ? nullptr : io.Yin + rowoff;
+    const T* __restrict__ pZ = FIRST ? nullptr : io.Zin + rowoff;
+    const double* __restrict__ pB = io.B + rowoff;
 
     const V zero = cheb_make2<T>(T(0), T(0));
-    V win[NLEV][3];      // level l: planes (old, mid, new) = (s-l-2, s-l-1, s-l)
+    V w[NLEV][3];        // level l: rotating window of three planes
     V bq[NLEV + 1];      // B at planes s, s-1, .., s-NLEV (cast to T)
     V zq = zero;         // Zin at plane s-1 (not FIRST)
 #pragma unroll
-    for (int l = 0; l < NLEV; l++) { win[l][0] = zero; win[l][1] = zero; win[l][2] = zero; }
+    for (int l = 0; l < NLEV; l++) { w[l][0] = zero; w[l][1] = zero; w[l][2] = zero; }
 #pragma unroll
     for (int m = 0; m <= NLEV; m++) bq[m] = zero;
 
-    auto load_T = [&](const T* f, int k) -> V {
+    // predicated loads: no branch on the thread's own activity; the plane test is uniform over the CTA
+    auto load_T = [&](const T* p, int k) -> V {
         V v = zero;
         if (k >= rg.k0 && k < rg.k1) {
-            const T* p = f + rowoff + k * d.plane;
-            if (a0 && a1) v = *reinterpret_cast<const V*>(p);
-            else if (a0) v.x = p[0];
-            else if (a1) v.y = p[1];
+            const T* q = p + k * d.plane;
+            if (a0) v.x = __ldg(q);
+            if (a1) v.y = __ldg(q + 1);
         }
         return v;
     };
     auto load_B = [&](int k) -> V {
         V v = zero;
         if (k >= rg.k0 && k < rg.k1) {
-            const double* p = io.B + rowoff + k * d.plane;
-            if (a0 && a1) { const double2 t = __ldg(reinterpret_cast<const double2*>(p)); v.x = fm.cast_in(t.x); v.y = fm.cast_in(t.y); }
-            else if (a0) v.x = fm.cast_in(__ldg(p));
-            else if (a1) v.y = fm.cast_in(__ldg(p + 1));
+            const double* q = pB + k * d.plane;
+            if (a0) v.x = fm.cast_in(__ldg(q));
+            if (a1) v.y = fm.cast_in(__ldg(q + 1));
         }
         return v;
     };
@@ -200,20 +208,23 @@ __global__ void __launch_bounds__(32 * FY) cheb_blocked_kernel(Dims d, Box rg, C
     const int s0 = ka - NLEV, s1 = kb - 1 + NLEV;   // march steps: level 0 touches planes s0 .. s1, level NLEV planes ka .. kb-1
     // two planes of prefetch for everything that is read from HBM
     V pf_f[2], pf_b[2] = {zero, zero}, pf_z[2] = {zero, zero};
-    pf_f[0] = FIRST ? load_B(s0) : load_T(io.Yin, s0);
-    pf_f[1] = FIRST ? load_B(s0 + 1) : load_T(io.Yin, s0 + 1);
+    pf_f[0] = FIRST ? load_B(s0) : load_T(pF, s0);
+    pf_f[1] = FIRST ? load_B(s0 + 1) : load_T(pF, s0 + 1);
     if (!FIRST) {
         pf_b[0] = load_B(s0); pf_b[1] = load_B(s0 + 1);
-        pf_z[0] = load_T(io.Zin, s0); pf_z[1] = load_T(io.Zin, s0 + 1);
+        pf_z[0] = load_T(pZ, s0); pf_z[1] = load_T(pZ, s0 + 1);
     }
 
-    for (int s = s0; s <= s1; ++s) {
+    // one march step with window rotation R (compile time) and, for boundary CTAs, the x / y Neumann remaps
+    auto step = [&](auto Rc, auto REMAPc, int s, int xl0, int xh0, int xl1, int xh1, int yl, int yh) {
+        constexpr int R = decltype(Rc)::value, RM = (R + 2) % 3, RO = (R + 1) % 3;   // new, mid, old slots
+        constexpr bool REMAP = decltype(REMAPc)::value != 0;
         const int cur = s & 1, prv = cur ^ 1;
         // ---- level 0: the plane that arrives from HBM
         const V f0v = pf_f[0];
-        V zprev = zq;                        // Zin at plane s-1
+        const V zprev = zq;                  // Zin at plane s-1
         pf_f[0] = pf_f[1];
-        pf_f[1] = (s + 2 <= s1) ? (FIRST ? load_B(s + 2) : load_T(io.Yin, s + 2)) : zero;
+        pf_f[1] = FIRST ? load_B(s + 2) : load_T(pF, s + 2);
 #pragma unroll
         for (int m = NLEV; m > 0; m--) bq[m] = bq[m - 1];
         if (FIRST) {
@@ -222,73 +233,100 @@ __global__ void __launch_bounds__(32 * FY) cheb_blocked_kernel(Dims d, Box rg, C
             bq[0] = pf_b[0];
             zq = pf_z[0];
             pf_b[0] = pf_b[1]; pf_z[0] = pf_z[1];
-            pf_b[1] = (s + 2 <= s1) ? load_B(s + 2) : zero;
-            pf_z[1] = (s + 2 <= s1) ? load_T(io.Zin, s + 2) : zero;
+            pf_b[1] = load_B(s + 2);
+            pf_z[1] = load_T(pZ, s + 2);
         }
-        win[0][0] = win[0][1]; win[0][1] = win[0][2]; win[0][2] = f0v;
+        w[0][R] = f0v;
         *reinterpret_cast<V*>(&plane[0][cur][row][2 * lane]) = f0v;
 
         // ---- levels 1 .. NLEV, each one plane behind the previous
 #pragma unroll
         for (int l = 1; l <= NLEV; l++) {
             const int k = s - l;
-            const V c = win[l - 1][1], zmv = win[l - 1][0], zpv = win[l - 1][2];
+            const V c = w[l - 1][RM], zmv = w[l - 1][RO], zpv = w[l - 1][R];
             const V ymv = *reinterpret_cast<const V*>(&plane[l - 1][prv][rm][2 * lane]);
             const V ypv = *reinterpret_cast<const V*>(&plane[l - 1][prv][rp][2 * lane]);
-            T xl = __shfl_up_sync(kFullMask, c.y, 1);
-            T xr = __shfl_down_sync(kFullMask, c.x, 1);
-            if (lane == 0) xl = T(0);
-            if (lane == 31) xr = T(0);
-            // neighbours of my two cells with the Neumann remaps
+            const T xl = __shfl_up_sync(kFullMask, c.y, 1);     // lane 0 / 31: a halo column, any value will do
+            const T xr = __shfl_down_sync(kFullMask, c.x, 1);
             T xm0 = xl, xp0 = c.y, xm1 = c.x, xp1 = xr;
-            if (xl0) xm0 = (xl0 == 2) ? xp0 : c.x;
-            if (xh0) xp0 = (xh0 == 2) ? xm0 : c.x;
-            if (xl1) xm1 = (xl1 == 2) ? xp1 : c.y;
-            if (xh1) xp1 = (xh1 == 2) ? xm1 : c.y;
             T ym0 = ymv.x, yp0 = ypv.x, ym1 = ymv.y, yp1 = ypv.y;
-            if (yl) { ym0 = (yl == 2) ? yp0 : c.x; ym1 = (yl == 2) ? yp1 : c.y; }
-            if (yh) { yp0 = (yh == 2) ? ym0 : c.x; yp1 = (yh == 2) ? ym1 : c.y; }
             T zm0 = zmv.x, zp0 = zpv.x, zm1 = zmv.y, zp1 = zpv.y;
-            const int zl = (k == 1) ? tl.nm[4] : 0, zh = (k == d.nz) ? tl.nm[5] : 0;
-            if (zl) { zm0 = (zl == 2) ? zp0 : c.x; zm1 = (zl == 2) ? zp1 : c.y; }
-            if (zh) { zp0 = (zh == 2) ? zm0 : c.x; zp1 = (zh == 2) ? zm1 : c.y; }
+            if (REMAP) {
+                // ghost value = opposite neighbour (orderNeumanBcs = 2) or the cell itself (= 1)
+                if (xl0) xm0 = (xl0 == 2) ? xp0 : c.x;
+                if (xh0) xp0 = (xh0 == 2) ? xm0 : c.x;
+                if (xl1) xm1 = (xl1 == 2) ? xp1 : c.y;
+                if (xh1) xp1 = (xh1 == 2) ? xm1 : c.y;
+                if (yl) { ym0 = (yl == 2) ? yp0 : c.x; ym1 = (yl == 2) ? yp1 : c.y; }
+                if (yh) { yp0 = (yh == 2) ? ym0 : c.x; yp1 = (yh == 2) ? ym1 : c.y; }
+            }
+            V z = zero;
+            if (!(FIRST && l == 1)) {
+                if (l == 1) z = zprev;                                                                       // y_{c0-1} from HBM
+                else if (FIRST && l == 2) z = cheb_make2<T>(fm.y0(w[0][RO].x), fm.y0(w[0][RO].y));           // y_0 = B / theta
+                else z = w[l >= 2 ? l - 2 : 0][RO];
+            }
+            auto eval = [&](T a_zm0, T a_zp0, T a_zm1, T a_zp1) -> V {
+                V r;
+                if (FIRST && l == 1) {
+                    r.x = fm.first(c.x, xm0, xp0, ym0, yp0, a_zm0, a_zp0);
+                    r.y = fm.first(c.y, xm1, xp1, ym1, yp1, a_zm1, a_zp1);
+                } else {
+                    r.x = fm.step(l, c.x, xm0, xp0, ym0, yp0, a_zm0, a_zp0, bq[l].x, z.x);
+                    r.y = fm.step(l, c.y, xm1, xp1, ym1, yp1, a_zm1, a_zp1, bq[l].y, z.y);
+                }
+                return r;
+            };
             V v;
-            if (FIRST && l == 1) {
-                v.x = fm.first(c.x, xm0, xp0, ym0, yp0, zm0, zp0);
-                v.y = fm.first(c.y, xm1, xp1, ym1, yp1, zm1, zp1);
+            const int zl = (k == 1) ? tl.nm[4] : 0, zh = (k == d.nz) ? tl.nm[5] : 0;   // uniform over the CTA, non-zero on two planes only
+            if (zl | zh) {
+                // rare path, evaluated on its own so that the common path carries no merges
+                if (zl) { zm0 = (zl == 2) ? zp0 : c.x; zm1 = (zl == 2) ? zp1 : c.y; }
+                if (zh) { zp0 = (zh == 2) ? zm0 : c.x; zp1 = (zh == 2) ? zm1 : c.y; }
+                v = eval(zm0, zp0, zm1, zp1);
             } else {
-                V z;
-                if (l == 1) z = zprev;                                                     // y_{c0-1} from HBM
-                else if (FIRST && l == 2) z = cheb_make2<T>(fm.y0(win[0][0].x), fm.y0(win[0][0].y));   // y_0 = B / theta
-                else z = win[l - 2][0];
-                v.x = fm.step(l, c.x, xm0, xp0, ym0, yp0, zm0, zp0, bq[l].x, z.x);
-                v.y = fm.step(l, c.y, xm1, xp1, ym1, yp1, zm1, zp1, bq[l].y, z.y);
+                v = eval(zmv.x, zpv.x, zmv.y, zpv.y);
             }
             const bool kin = k >= rg.k0 && k < rg.k1;
-            if (!(kin && a0)) v.x = T(0);
-            if (!(kin && a1)) v.y = T(0);
+            v.x = (kin && a0) ? v.x : T(0);
+            v.y = (kin && a1) ? v.y : T(0);
             if (l < NLEV) {
-                win[l][0] = win[l][1]; win[l][1] = win[l][2]; win[l][2] = v;
-                *reinterpret_cast<V*>(&plane[l][cur][row][2 * lane]) = v;
+                w[l < NLEV ? l : 0][R] = v;
+                *reinterpret_cast<V*>(&plane[l < NLEV ? l : 0][cur][row][2 * lane]) = v;
             } else if (k >= ka && k < kb && (o0 || o1)) {
                 const long long idx = rowoff + k * d.plane;
                 if (LAST) {
                     st2(io.X + idx, make_double2(fm.out_x(v.x), fm.out_x(v.y)), o0, o1);
                 } else {
                     // y_{c0+NLEV} and y_{c0+NLEV-1} at plane k
-                    V zo = (FIRST && NLEV == 1) ? cheb_make2<T>(fm.y0(win[0][1].x), fm.y0(win[0][1].y)) : win[NLEV - 1][1];
-                    if (o0 && o1) {
-                        *reinterpret_cast<V*>(io.Yout + idx) = v;
-                        *reinterpret_cast<V*>(io.Zout + idx) = zo;
-                    } else if (o0) {
-                        io.Yout[idx] = v.x; io.Zout[idx] = zo.x;
-                    } else {
-                        io.Yout[idx + 1] = v.y; io.Zout[idx + 1] = zo.y;
-                    }
+                    const V zo = (FIRST && NLEV == 1) ? cheb_make2<T>(fm.y0(w[0][RM].x), fm.y0(w[0][RM].y)) : w[NLEV - 1][RM];
+                    if (o0) { io.Yout[idx] = v.x; io.Zout[idx] = zo.x; }
+                    if (o1) { io.Yout[idx + 1] = v.y; io.Zout[idx + 1] = zo.y; }
                 }
             }
         }
         __syncthreads();
+    };
+
+    // does this CTA's footprint touch a Neumann face in x or y?  (uniform)
+    const int fx0 = ox - tl.le, fx1 = fx0 + 63, fy0 = oy - NLEV, fy1 = fy0 + FY - 1;
+    const bool remap = (tl.nm[0] && fx0 <= 1 && 1 <= fx1) || (tl.nm[1] && fx0 <= d.nx && d.nx <= fx1) ||
+                       (tl.nm[2] && fy0 <= 1 && 1 <= fy1) || (tl.nm[3] && fy0 <= d.ny && d.ny <= fy1);
+    if (remap) {
+        const int xl0 = (i0 == 1) ? tl.nm[0] : 0, xh0 = (i0 == d.nx) ? tl.nm[1] : 0;
+        const int xl1 = (i0 + 1 == 1) ? tl.nm[0] : 0, xh1 = (i0 + 1 == d.nx) ? tl.nm[1] : 0;
+        const int yl = (j == 1) ? tl.nm[2] : 0, yh = (j == d.ny) ? tl.nm[3] : 0;
+        for (int s = s0; s <= s1; s += 3) {
+            step(ChebInt<0>{}, ChebInt<1>{}, s, xl0, xh0, xl1, xh1, yl, yh);
+            step(ChebInt<1>{}, ChebInt<1>{}, s + 1, xl0, xh0, xl1, xh1, yl, yh);
+            step(ChebInt<2>{}, ChebInt<1>{}, s + 2, xl0, xh0, xl1, xh1, yl, yh);
+        }
+    } else {
+        for (int s = s0; s <= s1; s += 3) {
+            step(ChebInt<0>{}, ChebInt<0>{}, s, 0, 0, 0, 0, 0, 0);
+            step(ChebInt<1>{}, ChebInt<0>{}, s + 1, 0, 0, 0, 0, 0, 0);
+            step(ChebInt<2>{}, ChebInt<0>{}, s + 2, 0, 0, 0, 0, 0, 0);
+        }
     }
 }
 

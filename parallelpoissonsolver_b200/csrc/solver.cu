@@ -106,7 +106,7 @@ struct pps_handle {
     int by = 8;                 // tile rows of the plain-load kernels
     int stencil_impl = 1;       // 0 plain loads, 1 TMA ring (stencil_tma.cuh)
     int by_tma = 8;             // tile rows of the TMA operator kernels (8 or 16)
-    int occ_hint = 3;           // CTAs per SM of the operator kernel whose tiling is being made (see make_tiling)
+    int zchunk_hint = 0;        // z-chunk of the operator kernel whose tiling is being made, 0 = default (see make_tiling)
     int tma_l2_promo = 3;       // PPS_TMA_L2PROMO: 0 none, 1 64 B, 2 128 B, 3 256 B (tuning sweeps)
     int zchunk_fused_p = 0, zchunk_fused_s = 0;   // PPS_ZCHUNK_FUSED_P / _S: z-chunk of the two fused kernels (0 = the operator kernels' value)
     std::map<std::pair<const void*, int>, CUtensorMap> tmaps;   // key: (field, rows) main box; (field, -rows) aux box
@@ -117,7 +117,7 @@ struct pps_handle {
     bool operator_only = false; // PPS_FLAG_OPERATOR_ONLY: only p, v, r0 exist
     bool fuse_full = false;     // 17-pass schedule (single block, all-Dirichlet, no preconditioner)
     bool fuse_p = true, fuse_s = true;   // PPS_FUSE_P / PPS_FUSE_S: enable the two fused kernels separately (diagnostics)
-    int fuse_stages_p = 4, fuse_stages_s = 6;   // ring depth of the two fused kernels (PPS_FUSE_STAGES_P = 3|4, PPS_FUSE_STAGES_S = 3|4|6: tuning sweeps)
+    int fuse_stages_p = 3, fuse_stages_s = 4;   // ring depth of the two fused kernels (PPS_FUSE_STAGES_P = 3|4, PPS_FUSE_STAGES_S = 3|4|6: tuning sweeps)
     int fuse_check = 0;                  // PPS_FUSE_CHECK=1 (with PPS_FUSE_P=0): verify every fused_s launch against the split kernels
     int fuse_check_events = 0;
     int iter_in_solve = 0;      // host-side count of enqueued iterations of the running solve
@@ -154,18 +154,19 @@ struct pps_handle {
     bool cheb_f32 = false;            // mixed-precision preconditioner: iterates in fp32 (alpaka tree, T_data_chebyshev = float)
     bool precond_comm = false;        // Chebyshev preconditioner with communicationON: faces of B and of every iterate are exchanged
     bool cheb_eig_local = false;      // block-local, not rescaled eigenvalue bounds (alpaka tree inputParam.hpp:21-22 `local`)
-    int batch_ghosts = 0;             // PPS_BATCH_GHOSTS=1: all Neumann faces of a block in one launch (unverified, round 2)
-    // PPS_GRAPH=1 (unverified, round 2): one Krylov iteration is captured into a CUDA graph at its first launch and replayed;
+    int batch_ghosts = 1;             // all Neumann faces of a block in one launch (PPS_BATCH_GHOSTS=0: one launch per face)
+    // PPS_GRAPH (default for launch-bound problems on one GPU): one Krylov iteration is captured into a CUDA graph at its first launch and replayed;
     // every iteration enqueues the same kernels with the same arguments (the scalars live in `ctl` on the device)
     bool use_graph = false;
     cudaGraphExec_t iter_graph = nullptr;
     long long iter_graph_launches = 0;   // kernels per replay (for pps_get_launch_count)
     // peer-memory halo path (PPS_HALO_P2P=1, z-slabs): neighbours' field / flag arrays mapped through CUDA IPC
     bool p2p = false;
-    double* peer_field[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [lo/hi neighbour][0 = Mp, 1 = z]
+    std::vector<const double*> p2p_local;            // my arrays that neighbours may push into (r, p, p2, v, v2, Mp, z)
+    std::vector<double*> p2p_peer[2];                // the same arrays of my lower / upper z-neighbour, mapped here
     unsigned int* peer_flags[2] = {nullptr, nullptr};                      // neighbour's recv_epoch array
-    unsigned int* recv_epoch = nullptr;                                    // mine: [field][face lo/hi], written by the neighbours
-    unsigned int field_epoch[2] = {0, 0};
+    unsigned int* recv_epoch = nullptr;                                    // mine: [exchange slot][face lo/hi], written by the neighbours
+    unsigned int field_epoch[2] = {0, 0};            // per exchange slot: 0 = before the first operator of an iteration, 1 = before the second
     unsigned int* epoch_ring = nullptr;   // pinned host: source words of the flag DMAs (the host runs a few exchanges ahead)
     unsigned int epoch_ring_next = 0;
     std::vector<void*> ipc_opened;
@@ -290,22 +291,12 @@ static Tiling make_tiling(const pps_handle* h, const BlockGeom& g, const Box& bo
     int zc = stencil ? h->zchunk_stencil : h->zchunk_point;
     if (zc <= 0) {
         if (stencil) {
-            // Two costs decide the chunk length (profiles/README.md, round-2 sweep): every chunk re-reads two halo planes
-            // (zc / (zc + 2)), and the last wave of CTAs leaves SMs idle (waves / ceil(waves), waves = CTAs / (148 x CTAs
-            // resident per SM of the kernel about to be launched, `occ_hint`)).  At 512^3 this model ranks the measured
-            // variants correctly: fused_s (3 CTAs/SM) 32 planes 0.799 ms < 16 planes 0.814 < 64 planes 0.817; fused_p
-            // (2 CTAs/SM) 64 planes 1.081 ms < 32 planes 1.125.
-            const double slots = 148.0 * std::max(1, h->occ_hint);
-            double best = -1;
-            zc = std::min(nzb, 32);
-            for (int nch = 1; nch <= nzb; nch++) {
-                const int c = (nzb + nch - 1) / nch;
-                if (c < std::min(nzb, 12)) break;
-                if (c > 192) continue;
-                const double waves = static_cast<double>(gx) * gy * ((nzb + c - 1) / c) / slots;
-                const double score = waves / std::ceil(waves) * c / (c + 2.0);
-                if (score > best + 1e-9) { best = score; zc = c; }
-            }
+            // measured on B200 at 512^3 (profiles/README.md, r01 / r02 sweeps): fused_s 16 / 32 / 43 / 64 / 85 / 128 planes per chunk
+            // -> 0.814 / 0.799 / 0.810 / 0.817 / 0.859 / 0.892 ms, plain operator alike: short chunks win although every chunk
+            // re-reads two halo planes (they are still in L2 from the neighbouring chunk; z is the slowest grid dimension).  A model
+            // of wave quantisation + halo overhead picked 85 / 128 and was measurably worse.  fused_p (three halo'd inputs, its ring
+            // limits the SM to 2-3 CTAs) is the exception: 1.094 / 1.076 / 1.063 / 1.085 ms at 32 / 48 / 85 / 102 planes (3 ring stages) -> `zchunk_hint`.
+            zc = h->zchunk_hint > 0 ? h->zchunk_hint : 32;
         } else {
             // pointwise kernels have no halo: ~6 waves of CTAs (148 SMs x 8 CTAs of 256 threads), chunks >= 8 planes
             const long long target = 148LL * 8 * 6;
@@ -594,63 +585,99 @@ static void halo_exchange(pps_handle* h, FieldSel sel, bool check_done, bool on_
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned int kEpochRing = 4096;   // flag DMAs in flight are bounded by the host's run-ahead (PPS_LAG iterations)
 
+constexpr int kP2pMaxFields = 8;
 struct PeerInfo {
     long long pid;
     int device;
+    int nfields;
+    int ok;
     int pad;
-    cudaIpcMemHandle_t mp, z, flags;
-    unsigned long long raw_mp, raw_z, raw_flags;
+    cudaIpcMemHandle_t field[kP2pMaxFields], flags;
+    unsigned long long raw_field[kP2pMaxFields], raw_flags;
 };
 
+// Every rank offers the arrays whose guard planes its z-neighbours fill (same list, same order on every rank) and maps its
+// neighbours' arrays.  Any failure (CUDA IPC not permitted, no peer access) on ANY rank switches the transport off on ALL
+// ranks -- the NCCL exchange stays the fallback -- so the ranks can never disagree about which path an exchange takes.
 static void setup_p2p(pps_handle* h) {
     Block& b = h->blocks[0];
     for (int f = 0; f < 4; f++)
         if (b.g.hc[f]) return;   // x / y faces would need packing: NCCL path
     if (!(b.g.hc[4] || b.g.hc[5]) || h->cfg.solver != PPS_SOLVER_BICGSTAB) return;
-    PPS_CUDA_CHECK(cudaMalloc(&h->recv_epoch, 4 * sizeof(unsigned int)));
-    PPS_CUDA_CHECK(cudaMemsetAsync(h->recv_epoch, 0, 4 * sizeof(unsigned int), h->stream));
-    PPS_CUDA_CHECK(cudaHostAlloc(&h->epoch_ring, kEpochRing * sizeof(unsigned int), cudaHostAllocDefault));
+    std::vector<double*> offer = {b.r, b.p, b.p2, b.v, b.v2, b.mp, b.z};
+    std::vector<double*> uniq;
+    for (double* q : offer)
+        if (q != nullptr && std::find(uniq.begin(), uniq.end(), q) == uniq.end()) uniq.push_back(q);
+    const size_t sz = sizeof(PeerInfo);
+    if (sz * h->world > sizeof(double) * kMaxAcc * static_cast<size_t>(h->partial_capacity)) return;
     PeerInfo mine{};
     mine.pid = static_cast<long long>(getpid());
     mine.device = h->device;
-    PPS_CUDA_CHECK(cudaIpcGetMemHandle(&mine.mp, b.mp));
-    PPS_CUDA_CHECK(cudaIpcGetMemHandle(&mine.z, b.z));
-    PPS_CUDA_CHECK(cudaIpcGetMemHandle(&mine.flags, h->recv_epoch));
-    mine.raw_mp = reinterpret_cast<unsigned long long>(b.mp);
-    mine.raw_z = reinterpret_cast<unsigned long long>(b.z);
+    mine.nfields = static_cast<int>(uniq.size());
+    mine.ok = 1;
+    if (cudaMalloc(&h->recv_epoch, 4 * sizeof(unsigned int)) != cudaSuccess) { mine.ok = 0; h->recv_epoch = nullptr; }
+    if (mine.ok) PPS_CUDA_CHECK(cudaMemsetAsync(h->recv_epoch, 0, 4 * sizeof(unsigned int), h->stream));
+    if (mine.ok && cudaHostAlloc(&h->epoch_ring, kEpochRing * sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess) { mine.ok = 0; h->epoch_ring = nullptr; }
+    for (int q = 0; mine.ok && q < mine.nfields; q++) {
+        if (cudaIpcGetMemHandle(&mine.field[q], uniq[q]) != cudaSuccess) mine.ok = 0;
+        mine.raw_field[q] = reinterpret_cast<unsigned long long>(uniq[q]);
+    }
+    if (mine.ok && cudaIpcGetMemHandle(&mine.flags, h->recv_epoch) != cudaSuccess) mine.ok = 0;
     mine.raw_flags = reinterpret_cast<unsigned long long>(h->recv_epoch);
-    const size_t sz = sizeof(PeerInfo);
-    if (sz * h->world > sizeof(double) * kMaxAcc * static_cast<size_t>(h->partial_capacity)) return;
+    cudaGetLastError();
     char* scratch = reinterpret_cast<char*>(h->partials);
     PPS_CUDA_CHECK(cudaMemcpyAsync(scratch + sz * h->rank, &mine, sz, cudaMemcpyHostToDevice, h->stream));
     PPS_NCCL_CHECK(nccl().AllGather(scratch + sz * h->rank, scratch, sz, ncclChar, h->comm, h->stream));
     std::vector<PeerInfo> all(h->world);
     PPS_CUDA_CHECK(cudaMemcpyAsync(all.data(), scratch, sz * h->world, cudaMemcpyDeviceToHost, h->stream));
     PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    for (int up = 0; up < 2; up++) {
+    bool ok = true;
+    for (auto& pi : all) ok = ok && pi.ok && pi.nfields == mine.nfields;
+    for (int up = 0; ok && up < 2; up++) {
         if (!b.g.hc[4 + up]) continue;
         const PeerInfo& pi = all[b.g.nbr[4 + up]];
+        h->p2p_peer[up].assign(uniq.size(), nullptr);
         if (pi.pid == mine.pid) {
             // rank-threads of one process (C++ driver): plain peer access
             if (pi.device != h->device) {
                 cudaError_t e = cudaDeviceEnablePeerAccess(pi.device, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PPS_CUDA_CHECK(e);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
                 cudaGetLastError();
             }
-            h->peer_field[up][0] = reinterpret_cast<double*>(pi.raw_mp);
-            h->peer_field[up][1] = reinterpret_cast<double*>(pi.raw_z);
+            for (size_t q = 0; q < uniq.size(); q++) h->p2p_peer[up][q] = reinterpret_cast<double*>(pi.raw_field[q]);
             h->peer_flags[up] = reinterpret_cast<unsigned int*>(pi.raw_flags);
         } else {
-            void* q = nullptr;
-            PPS_CUDA_CHECK(cudaIpcOpenMemHandle(&q, pi.mp, cudaIpcMemLazyEnablePeerAccess));
-            h->peer_field[up][0] = static_cast<double*>(q); h->ipc_opened.push_back(q);
-            PPS_CUDA_CHECK(cudaIpcOpenMemHandle(&q, pi.z, cudaIpcMemLazyEnablePeerAccess));
-            h->peer_field[up][1] = static_cast<double*>(q); h->ipc_opened.push_back(q);
-            PPS_CUDA_CHECK(cudaIpcOpenMemHandle(&q, pi.flags, cudaIpcMemLazyEnablePeerAccess));
-            h->peer_flags[up] = static_cast<unsigned int*>(q); h->ipc_opened.push_back(q);
+            void* ptr = nullptr;
+            for (size_t q = 0; ok && q < uniq.size(); q++) {
+                if (cudaIpcOpenMemHandle(&ptr, pi.field[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+                h->p2p_peer[up][q] = static_cast<double*>(ptr); h->ipc_opened.push_back(ptr);
+            }
+            if (ok && cudaIpcOpenMemHandle(&ptr, pi.flags, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+                h->peer_flags[up] = static_cast<unsigned int*>(ptr); h->ipc_opened.push_back(ptr);
+            } else {
+                ok = false;
+            }
+            cudaGetLastError();
         }
     }
+    // agree: one more collective (also the barrier after which nobody's flags are cleared any more)
+    double flag = ok ? 0.0 : 1.0;
+    PPS_CUDA_CHECK(cudaMemcpyAsync(h->ctl->sums + 7, &flag, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    PPS_NCCL_CHECK(nccl().AllReduce(h->ctl->sums + 7, h->ctl->sums + 7, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    PPS_CUDA_CHECK(cudaMemcpyAsync(&flag, h->ctl->sums + 7, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (flag != 0.0) {
+        if (h->rank == 0 && env_int("PPS_VERBOSE", 0)) std::fprintf(stderr, "[pps] peer-memory halo transport not available: using NCCL send/recv\n");
+        return;
+    }
+    h->p2p_local.assign(uniq.begin(), uniq.end());
     h->p2p = true;
+}
+
+static int p2p_index(const pps_handle* h, const double* f) {
+    for (size_t q = 0; q < h->p2p_local.size(); q++)
+        if (h->p2p_local[q] == f) return static_cast<int>(q);
+    return -1;
 }
 
 // mailboxes of the in-kernel allreduce: exchange IPC handles with EVERY rank
@@ -696,23 +723,28 @@ static void setup_allreduce_p2p(pps_handle* h) {
     h->ar_p2p = true;
 }
 
-// push my boundary planes of field `fidx` (0 = Mp, 1 = z) into the neighbours' guard planes on the halo stream
-static unsigned int halo_push_p2p(pps_handle* h, int fidx, double* fld) {
+// push my boundary planes of every field of `fs` into the neighbours' guard planes on the halo stream; `slot` names the exchange
+// (0: before the first operator of an iteration, 1: before the second) and with it the pair of epoch flags
+static unsigned int halo_push_p2p(pps_handle* h, int slot, const FieldSet& fs) {
     Block& b = h->blocks[0];
-    const unsigned int epoch = ++h->field_epoch[fidx];
+    const unsigned int epoch = ++h->field_epoch[slot];
     LaunchScope ls(h, KC_HALO);
     for (int up = 0; up < 2; up++) {
         if (!b.g.hc[4 + up]) continue;
         const long long kdata = up ? b.g.n[2] : 1;                 // my boundary data plane
         const long long kguard = up ? 0 : b.g.n[2] + 1;            // the neighbour's guard plane that faces me
-        PPS_CUDA_CHECK(cudaMemcpyAsync(h->peer_field[up][fidx] + kguard * b.g.dims.plane, fld + kdata * b.g.dims.plane,
-                                       sizeof(double) * static_cast<size_t>(b.g.dims.plane), cudaMemcpyDefault, h->halo_stream));
+        for (int q = 0; q < fs.n; q++) {
+            double* fld = fs.sel[q](b);
+            double* peer = h->p2p_peer[up][p2p_index(h, fld)];
+            PPS_CUDA_CHECK(cudaMemcpyAsync(peer + kguard * b.g.dims.plane, fld + kdata * b.g.dims.plane,
+                                           sizeof(double) * static_cast<size_t>(b.g.dims.plane), cudaMemcpyDefault, h->halo_stream));
+        }
         // my upper neighbour receives on ITS lower face (slot 0), my lower neighbour on its upper face (slot 1).  The flag is a
-        // second DMA (4 bytes from a pinned host word) ordered after the plane by the stream: no SM takes part in the
+        // last DMA (4 bytes from a pinned host word) ordered after the planes by the stream: no SM takes part in the
         // transport, so receivers may wait inside a running kernel (PPS_OVERLAP=3) without starving the sender.
         unsigned int* word = h->epoch_ring + (h->epoch_ring_next++ % kEpochRing);
         *word = epoch;
-        PPS_CUDA_CHECK(cudaMemcpyAsync(h->peer_flags[up] + 2 * fidx + (up ? 0 : 1), word, sizeof(unsigned int), cudaMemcpyDefault,
+        PPS_CUDA_CHECK(cudaMemcpyAsync(h->peer_flags[up] + 2 * slot + (up ? 0 : 1), word, sizeof(unsigned int), cudaMemcpyDefault,
                                        h->halo_stream));
     }
     check_launch("halo_push_p2p");
@@ -985,6 +1017,13 @@ static void nested_iterations(pps_handle* h, Block& b, EnqueueIteration&& enqueu
             if (b.ihist_host[it - lag + 1] < h->precond_tolerance) { done_at = it - lag + 1; break; }
         }
     }
+    if (done_at == h->precond_max_iter) {
+        // the host looks `lag` iterations late: a solve that converged within the last `lag` iterations has not been seen yet.
+        // The device stopped at the right iteration (every kernel honours the nested `done`); read the true count for the report.
+        PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        for (int it = std::max(0, h->precond_max_iter - lag); it < h->precond_max_iter; ++it)
+            if (b.ihist_host[it + 1] < h->precond_tolerance) { done_at = it + 1; break; }
+    }
     h->precond_iters += done_at;
 }
 
@@ -1251,7 +1290,7 @@ static bool box_empty(const Box& b) { return b.i0 >= b.i1 || b.j0 >= b.j1 || b.k
 // `launch(block, box, tiling, red)` enqueues the operator kernel on h->launch_stream for a sub-box of the block.
 // `plain_stencil`: the launch goes through launch_stencil, i.e. the in-kernel-wait / peer-transport schedules may be used.
 template <class Launch>
-static void overlapped_operator(pps_handle* h, const FieldSet& xchg, const FieldSet& ghost, int nacc, int op, bool plain_stencil,
+static void overlapped_operator(pps_handle* h, const FieldSet& xchg, const FieldSet& ghost, int nacc, int op, bool plain_stencil, int slot,
                                 Launch launch) {
     bool any_comm = false;
     for (int f = 0; f < 6; f++) any_comm = any_comm || h->blocks[0].g.hc[f];
@@ -1272,16 +1311,16 @@ static void overlapped_operator(pps_handle* h, const FieldSet& xchg, const Field
         Block& b = h->blocks[0];
         PPS_CUDA_CHECK(cudaEventRecord(h->ev_field_ready, h->stream));
         PPS_CUDA_CHECK(cudaStreamWaitEvent(h->halo_stream, h->ev_field_ready, 0));
-        const FieldSel sel = xchg.sel[0];
-        const bool use_p2p = h->p2p && plain_stencil && xchg.n == 1 && (sel == sel_mp || sel == sel_z);
+        bool use_p2p = h->p2p && slot >= 0;
+        for (int q = 0; q < xchg.n; q++) use_p2p = use_p2p && p2p_index(h, xchg.sel[q](b)) >= 0;
         unsigned int p2p_epoch = 0;
-        const int p2p_field = sel == sel_z ? 1 : 0;
-        if (use_p2p) p2p_epoch = halo_push_p2p(h, p2p_field, sel(b));
+        const int p2p_field = slot;
+        if (use_p2p) p2p_epoch = halo_push_p2p(h, slot, xchg);
         else halo_exchange(h, xchg, true, /*on_halo_stream=*/true);
         const bool z_only = !(b.g.hc[0] || b.g.hc[1] || b.g.hc[2] || b.g.hc[3]);
         for (int q = 0; q < ghost.n; q++) neumann_ghosts(h, b, ghost.sel[q](b), false, true);
         const Tiling t_all = make_tiling(h, b.g, b.g.solver_box(), true);
-        if (use_p2p && h->stencil_impl == 1 && h->overlap == 3 && t_all.grid.z >= 3) {
+        if (use_p2p && plain_stencil && h->stencil_impl == 1 && h->overlap == 3 && t_all.grid.z >= 3) {
             // EXPERIMENTAL (PPS_OVERLAP=3, needs PPS_HALO_P2P=1): ONE launch; the TMA producers of the first / last z-chunk wait
             // in-kernel for the neighbours' epoch flags.  Unlike PPS_OVERLAP=2 the transport is pure DMA (halo_push_p2p), so the
             // waiting CTAs cannot keep a communication kernel off the SMs.
@@ -1349,7 +1388,10 @@ static void overlapped_operator(pps_handle* h, const FieldSet& xchg, const Field
 // the plain operator kernels: exchange + ghosts on the operand itself
 template <class MakeEpi>
 static void fused_operator(pps_handle* h, int kc, FieldSel sel, bool ghosts, int nacc, int op, MakeEpi make_epi) {
-    overlapped_operator(h, FieldSet(sel), ghosts ? FieldSet(sel) : FieldSet(), nacc, op, true,
+    // exchange slot of the peer transport: the operand of the second operator of a BiCGSTAB iteration is z (or r when fused
+    // schedules fall back to the plain kernel); everything else is "first"; fields the peers do not map go over NCCL
+    const int slot = (sel == sel_z || sel == sel_r) ? 1 : 0;
+    overlapped_operator(h, FieldSet(sel), ghosts ? FieldSet(sel) : FieldSet(), nacc, op, true, slot,
                         [&](Block& b, const Box& box, const Tiling& t, const RedCtx& red) {
                             launch_stencil(h, kc, b, sel(b), box, make_epi(b), red, t, true);
                         });
@@ -1373,9 +1415,7 @@ static void bicgstab_iteration(pps_handle* h) {
     // z = M(r); halo(z); ghosts(z); t = A z; sum r.t, t.t; omega             :181-225
     precondition_all(h, sel_z, sel_r, true);
     if (h->blocks[0].z == h->blocks[0].r) {
-        h->occ_hint = 4;   // no aux stream: 34.6 KB of shared memory per CTA
         fused_operator(h, KC_APPLY_DOT2, sel_z, true, 2, OP_BICG_OMEGA, [](Block& b) { return EpiStoreDot2Self{b.t}; });
-        h->occ_hint = 3;
     } else {
         fused_operator(h, KC_APPLY_DOT2, sel_z, true, 2, OP_BICG_OMEGA, [](Block& b) { return EpiStoreDot2{b.t, b.r}; });
     }
@@ -1445,13 +1485,14 @@ static void bicgstab_iteration_fused(pps_handle* h) {
     if (!first && h->fuse_p) {
         // p' = r + beta (p - omega v) ; v' = A p' ; sum r0.v' ; alpha            :262-272 of the previous pass + :142-164
         const FieldSet in = h->fuse_s ? FieldSet(sel_r, sel_p) : FieldSet(sel_r, sel_p, sel_v);
-        h->occ_hint = h->fuse_stages_p == 3 ? 3 : 2;   // 85.5 KB (4 stages) / 64 KB (3 stages) of shared memory per CTA
-        overlapped_operator(h, in, in, 1, OP_BICG_ALPHA, false, [&](Block& b, const Box& box, const Tiling& t, const RedCtx& red) {
+        // longer chunks for fused_p where the block is deep enough to keep an interior box of several chunks
+        h->zchunk_hint = h->zchunk_fused_p > 0 ? h->zchunk_fused_p : (h->blocks[0].g.n[2] >= 256 ? 85 : 0);
+        overlapped_operator(h, in, in, 1, OP_BICG_ALPHA, false, 0, [&](Block& b, const Box& box, const Tiling& t, const RedCtx& red) {
             if (parity) launch_tma_pre<8, 4, true>(h, KC_FUSED_P, b, box, PrePUpdate<true>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, t, true);
             else if (h->fuse_stages_p == 3) launch_tma_pre<8, 3, false>(h, KC_FUSED_P, b, box, PrePUpdate<false>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, t, true);
             else        launch_tma_pre<8, 4, false>(h, KC_FUSED_P, b, box, PrePUpdate<false>{b.p2, b.r, b.p, b.v, 0, 0}, EpiStoreDot{b.v2, b.r0}, red, t, true);
         });
-        h->occ_hint = 3;
+        h->zchunk_hint = 0;
         for (auto& b : h->blocks) {
             std::swap(b.p, b.p2);
             std::swap(b.v, b.v2);
@@ -1473,7 +1514,7 @@ static void bicgstab_iteration_fused(pps_handle* h) {
     if (h->fuse_s) {
         {   // s = r - alpha v ; t = A s ; sum s.t, t.t ; omega                        :168-225
             const FieldSet in = (first || !h->fuse_p) ? FieldSet(sel_v, sel_r) : FieldSet(sel_v);
-            overlapped_operator(h, in, in, 2, OP_BICG_OMEGA, false, [&](Block& b, const Box& box, const Tiling& t, const RedCtx& red) {
+            overlapped_operator(h, in, in, 2, OP_BICG_OMEGA, false, 1, [&](Block& b, const Box& box, const Tiling& t, const RedCtx& red) {
                 if (parity) launch_tma_pre<8, 6, true>(h, KC_FUSED_S, b, box, PreSUpdate<true>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
                 else if (h->fuse_stages_s == 3) launch_tma_pre<8, 3, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
                 else if (h->fuse_stages_s == 4) launch_tma_pre<8, 4, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
@@ -1743,13 +1784,16 @@ static void validate(const pps_config& c, int rank, int world) {
                                  "(a global nested BiCGSTAB, alpaka inputParam.hpp:33, is not)");
 }
 
+static void destroy(pps_handle* h);
+
 static pps_handle* create(const pps_config& cfg, int rank, int world, const unsigned char* uid) {
     validate(cfg, rank, world);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         throw std::runtime_error(std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
-    std::unique_ptr<pps_handle> h(new pps_handle());
+    // any throw below (out of memory at large grids, NCCL bootstrap, peer mapping) releases what has been acquired so far
+    std::unique_ptr<pps_handle, void (*)(pps_handle*)> h(new pps_handle(), &destroy);
     h->cfg = cfg;
     h->rank = rank;
     h->world = world;
@@ -1763,10 +1807,11 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     h->zchunk_stencil = env_int("PPS_ZCHUNK_STENCIL", 0);
     h->zchunk_point = env_int("PPS_ZCHUNK_POINT", 0);
     h->tma_l2_promo = env_int("PPS_TMA_L2PROMO", 3);
+    h->zchunk_fused_p = env_int("PPS_ZCHUNK_FUSED_P", 0);
     h->lag = env_int("PPS_LAG", 3);
     h->overlap = env_int("PPS_OVERLAP", 1);
     h->debug_no_halo = env_int("PPS_DEBUG_NO_HALO", 0);
-    h->batch_ghosts = env_int("PPS_BATCH_GHOSTS", 0);
+    h->batch_ghosts = env_int("PPS_BATCH_GHOSTS", 1);   // all Neumann faces of a block in one launch (bitwise identical; validated on B200 in round 2)
     h->zchunk_cheb = env_int("PPS_ZCHUNK_CHEB", 0);
     // alpaka-only configuration surface: mixed-precision and local-eigenvalue Chebyshev preconditioner
     h->cheb_eig_local = env_int("PPS_CHEB_EIG_LOCAL", cfg.cheb_eigenvalues) == PPS_CHEB_EIG_LOCAL;
@@ -1774,8 +1819,11 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     h->cheb_block = std::max(0, std::min(env_int("PPS_CHEB_BLOCK", cfg.cheb_block), kChebMaxLev));
     h->precond_comm = cfg.precond_communication != 0;
     // graphs: one block-set on one GPU, iteration-invariant launches only (no ping-pong schedule, no host-synchronising nested solves)
-    h->use_graph = env_int("PPS_GRAPH", 0) != 0 && world == 1 && cfg.precond != PPS_PRECOND_BICGSTAB_LOCAL &&
-                   cfg.precond != PPS_PRECOND_CG_CHEB_LOCAL;
+    // Default: on for launch-bound problems (<= 2^25 cells on one GPU; the shipped 128x128x256 + Chebyshev default issues ~80 dependent
+    // launches per iteration: 0.097 s per solve with stream launches, 0.070 s with graph replay + batched ghosts, B200, round 2).
+    const long long cells_total = static_cast<long long>(cfg.npglobal[0]) * cfg.npglobal[1] * cfg.npglobal[2];
+    h->use_graph = env_int("PPS_GRAPH", cells_total <= (1LL << 25) ? 1 : 0) != 0 && world == 1 && cfg.precond != PPS_PRECOND_BICGSTAB_LOCAL &&
+                   cfg.precond != PPS_PRECOND_CG_CHEB_LOCAL && cfg.solver != PPS_SOLVER_CHEBYSHEV;
     PPS_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->launch_stream = h->stream;
     for (int d = 0; d < 3; d++) {
@@ -1806,13 +1854,12 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         for (int f = 0; f < 6; f++) neumann = neumann || cfg.bcs_type[f] == 1;
         (void)neumann;
         h->fuse_full = want != PPS_FUSE_SPLIT && cfg.dim == 3 && !has_precond && cfg.solver == PPS_SOLVER_BICGSTAB &&
-                       h->stencil_impl == 1 && h->by_tma == 8 &&
-                       !(world > 1 && env_int("PPS_HALO_P2P", 0));   // the peer transport maps Mp and z only (no ping-pong buffers)
+                       h->stencil_impl == 1 && h->by_tma == 8;
         h->fuse_p = env_int("PPS_FUSE_P", 1) != 0;
         h->fuse_s = env_int("PPS_FUSE_S", 1) != 0;
         h->fuse_check = env_int("PPS_FUSE_CHECK", 0);
-        h->fuse_stages_p = env_int("PPS_FUSE_STAGES_P", 4);
-        h->fuse_stages_s = env_int("PPS_FUSE_STAGES_S", 6);
+        h->fuse_stages_p = env_int("PPS_FUSE_STAGES_P", 3);   // 3 stages = 64 KB of ring = 3 CTAs per SM: 1.062 ms against 1.106 ms with 4 stages at 512^3
+        h->fuse_stages_s = env_int("PPS_FUSE_STAGES_S", 4);   // 46 KB of ring = 4 CTAs per SM: 0.789 ms against 0.799 ms with 6 stages at 512^3
     }
     unsigned long long max_ctas = 0;
     h->operator_only = (cfg.flags & PPS_FLAG_OPERATOR_ONLY) != 0;
@@ -1821,7 +1868,8 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     for (auto& b : h->blocks) {
         const long long n = b.g.dims.total;
         if (h->operator_only) {
-            b.p = dalloc(b, n, h->stream); b.v = dalloc(b, n, h->stream); b.r0 = dalloc(b, n, h->stream);
+            b.p = dalloc(b, n, h->stream); b.v = dalloc(b, n, h->stream);
+            if (!(cfg.flags & PPS_FLAG_NO_DOT_VECTOR)) b.r0 = dalloc(b, n, h->stream);
             b.mp = b.p;
             max_ctas += static_cast<unsigned long long>((b.g.n[0] + 63) / 64) * ((b.g.n[1] + 3) / 4) * b.g.n[2];
             continue;
@@ -1925,7 +1973,9 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         PPS_CUDA_CHECK(cudaMalloc(&h->halo_flag, sizeof(unsigned int)));
         PPS_CUDA_CHECK(cudaMemsetAsync(h->halo_flag, 0, sizeof(unsigned int), h->stream));
     }
-    if (world > 1 && env_int("PPS_HALO_P2P", 0) && h->overlap) setup_p2p(h.get());
+    // peer-memory face transport for z-slabs (copy engines + DMA-written epoch flags, no SM, no NCCL kernel): the default since
+    // round 2 (2 GPUs, 1024x1024x256: 90 % of the exchange hidden against 76 % over NCCL); PPS_HALO_P2P=0 forces NCCL send/recv
+    if (world > 1 && env_int("PPS_HALO_P2P", 1) && h->overlap) setup_p2p(h.get());
     if (world > 1 && world <= 256 && env_int("PPS_ALLREDUCE_P2P", 0)) setup_allreduce_p2p(h.get());
     h->ctl_host = Ctl{};
     h->ctl_host.norm_b = 1;
@@ -1937,7 +1987,7 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
 static void destroy(pps_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->halo_stream) cudaStreamSynchronize(h->halo_stream);
     if (h->comm_halo) nccl().CommDestroy(h->comm_halo);
     if (h->comm) nccl().CommDestroy(h->comm);
@@ -1959,15 +2009,20 @@ static void destroy(pps_handle* h) {
         if (b.ictl) cudaFree(b.ictl);
         if (b.ihist_host) cudaFreeHost(b.ihist_host);
     }
-    for (auto e : h->inner_events) cudaEventDestroy(e);
-    cudaFree(h->partials);
-    cudaFree(h->counter);
-    cudaFree(h->ctl);
-    for (int q = 0; q < 4; q++) cudaFreeHost(h->hist_host[q]);
+    for (auto e : h->inner_events)
+        if (e) cudaEventDestroy(e);
+    if (h->partials) cudaFree(h->partials);
+    if (h->counter) cudaFree(h->counter);
+    if (h->ctl) cudaFree(h->ctl);
+    for (int q = 0; q < 4; q++)
+        if (h->hist_host[q]) cudaFreeHost(h->hist_host[q]);
     for (auto e : h->event_pool) cudaEventDestroy(e);
-    for (auto e : h->iter_events) cudaEventDestroy(e);
-    cudaEventDestroy(h->ev_start); cudaEventDestroy(h->ev_loop0); cudaEventDestroy(h->ev_loop1); cudaEventDestroy(h->ev_end);
-    cudaStreamDestroy(h->stream);
+    for (auto e : h->iter_events)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->ev_start, h->ev_loop0, h->ev_loop1, h->ev_end})
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
     delete h;
 }
 
@@ -2179,6 +2234,7 @@ int pps_num_local_blocks(const pps_handle* h) { return h ? static_cast<int>(h->b
 
 int pps_block_info_get(const pps_handle* h, int rank, pps_block_info* out) {
     PPS_API_BEGIN
+    if (!h || !out) throw std::runtime_error("null argument");
     // geometry of ANY rank of the decomposition can be queried, hosted here or not
     const int nr = h->cfg.nranks[0] * h->cfg.nranks[1] * h->cfg.nranks[2];
     if (rank < 0 || rank >= nr) throw std::runtime_error("rank out of range");
@@ -2203,6 +2259,8 @@ int pps_block_info_get(const pps_handle* h, int rank, pps_block_info* out) {
 
 int pps_eigenvalues(const pps_handle* h, int rank, double g[2], double l[2]) {
     PPS_API_BEGIN
+    if (!h || !g || !l) throw std::runtime_error("null argument");
+    if (rank < 0 || rank >= h->cfg.nranks[0] * h->cfg.nranks[1] * h->cfg.nranks[2]) throw std::runtime_error("rank out of range");
     const BlockGeom b = make_block(h->cfg, rank);
     g[0] = b.eig_global[0]; g[1] = b.eig_global[1];
     l[0] = b.eig_local[0]; l[1] = b.eig_local[1];
@@ -2371,6 +2429,7 @@ int pps_bench_operator(pps_handle* h, int reps, int with_dot, double* avg_ms) {
     PPS_CUDA_CHECK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), h->stream));
     const bool with_halo = (with_dot & 2) != 0;
     with_dot &= 1;
+    if (with_dot && b.r0 == nullptr) throw std::runtime_error("pps_bench_operator: the handle has no dot-product vector (PPS_FLAG_NO_DOT_VECTOR)");
     auto once = [&]() {
         if (with_halo) halo_exchange(h, sel_p, false);
         if (with_dot) {

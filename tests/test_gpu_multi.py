@@ -60,17 +60,16 @@ def test_eight_gpus(layout):
     _run(layout, ("fusecmp",))
 
 
-EXPERIMENTAL = os.environ.get("PPS_TEST_EXPERIMENTAL") == "1"
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="experimental paths: set PPS_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("env", [{"PPS_HALO_P2P": "1"}, {"PPS_ALLREDUCE_P2P": "1"}, {"PPS_HALO_P2P": "1", "PPS_ALLREDUCE_P2P": "1"},
-                                 {"PPS_OVERLAP": "0"}, {"PPS_OVERLAP": "2"}, {"PPS_HALO_P2P": "1", "PPS_OVERLAP": "3"},
-                                 {"PPS_HALO_P2P": "1", "PPS_OVERLAP": "3", "PPS_ALLREDUCE_P2P": "1"}])
-@pytest.mark.parametrize("flags", [(), ("cheb",)])
+# transports and overlap schedules (validated on 2 B200s in round 2).  Default: peer-memory face pushes (CUDA IPC + copy engines,
+# PPS_HALO_P2P=1), three-stream overlap (PPS_OVERLAP=1), NCCL allreduce.
+@pytest.mark.parametrize("env", [{"PPS_HALO_P2P": "0"}, {"PPS_ALLREDUCE_P2P": "1"}, {"PPS_HALO_P2P": "0", "PPS_ALLREDUCE_P2P": "1"},
+                                 {"PPS_OVERLAP": "0"}, {"PPS_OVERLAP": "2", "PPS_HALO_P2P": "0"}, {"PPS_OVERLAP": "3"},
+                                 {"PPS_OVERLAP": "3", "PPS_ALLREDUCE_P2P": "1"}])
+@pytest.mark.parametrize("flags", [("fusecmp",), ("cheb",)])
 def test_two_gpus_slab_transport_variants(env, flags):
-    """the same parity check with the peer-memory halo path (CUDA IPC + copy engines), the serial exchange, the
-    in-kernel-wait overlap over NCCL (PPS_OVERLAP=2) and over the SM-free peer transport (PPS_OVERLAP=3)"""
+    """the same parity check over NCCL send/recv instead of the peer-memory pushes, with the in-kernel allreduce over peer
+    memory, with the serial exchange, and with the in-kernel-wait overlaps (PPS_OVERLAP=2 over NCCL, =3 over the SM-free
+    peer transport)"""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     _run((1, 1, 2), flags, env)

@@ -5,7 +5,7 @@ that fits, GB/s against the HBM roofline (16 algorithmic bytes per cell: read x,
     python tools/bandwidth_sweep.py [sizes ...]                      one GPU (operator-only handles: 3 vectors per size)
     torchrun --nproc-per-node N tools/bandwidth_sweep.py [sizes ...]  weak scaling: every rank owns an n^3 block of a 1x1xN
                                                                        slab decomposition; each apply is preceded by the z-face exchange
-The largest cube that fits: 3 vectors * 8 B * (n+17)(n+2)^2 <= ~170 GB  ->  n ~ 1900 (2 vectors would allow ~2180).
+The largest cube that fits: 3 vectors * 8 B * (n+17)(n+2)^2 <= ~170 GB  ->  n ~ 1850; with x and y only (no fused dot) 2176^3 = 165 GB.
 """
 import json
 import os
@@ -17,7 +17,7 @@ import parallelpoissonsolver_b200 as pps  # noqa: E402
 
 
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [64, 128, 192, 256, 384, 512, 640, 768, 1024, 1280, 1536, 1792]
+    sizes = [int(a) for a in sys.argv[1:]] or [64, 128, 192, 256, 384, 512, 640, 768, 1024, 1280, 1536, 1792, 2048, 2176]
     peak, src = bench.measured_peak()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     D = bench.Dist(rank, world, "cuda")
@@ -28,14 +28,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     for n in sizes:
         uid = D.bcast_bytes(pps.get_unique_id() if rank == 0 else None, 128) if world > 1 else None
+        two_vectors = 3 * 8 * (n + 17) * (n + 2) ** 2 > 165e9      # beyond ~1850^3 only x and y fit: no fused-dot variant
         try:
-            s = pps.PoissonSolver(pps.make_config((n, n, n * world), nranks=(1, 1, world), device=local, flags=pps.FLAG_OPERATOR_ONLY),
+            s = pps.PoissonSolver(pps.make_config((n, n, n * world), nranks=(1, 1, world), device=local,
+                                                  flags=pps.FLAG_OPERATOR_ONLY | (pps.FLAG_NO_DOT_VECTOR if two_vectors else 0)),
                                   rank=rank, world_size=world, unique_id=uid)
         except pps.PpsError as e:
             print(json.dumps(dict(n=n, error=str(e)[:200])), flush=True)
             break
         reps = max(5, min(200, int(2e9 / n ** 3)))
-        for dot in (False, True):
+        for dot in ((False,) if two_vectors else (False, True)):
             D.barrier()
             ms = D.max(s.bench_operator(reps, dot, with_halo=world > 1))
             nbytes = n ** 3 * 8 * (3 if dot else 2) * world

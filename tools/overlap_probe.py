@@ -6,7 +6,8 @@
 Three timed variants of the same fixed-length BiCGSTAB loop on 1x1xN z-slabs (SURVEY.md section 8d "Overlap metric"):
   no_comm   PPS_DEBUG_NO_HALO=1   faces never travel (wrong numbers, timing only)
   serial    PPS_OVERLAP=0         exchange, then the whole operator, on one stream
-  overlap   PPS_OVERLAP=1         exchange on the halo stream while the interior box is computed
+  overlap   PPS_OVERLAP=1         exchange (NCCL send/recv) on the halo stream while the interior box is computed
+  p2p       + PPS_HALO_P2P=1      the default: the same schedule with the faces pushed into the neighbours' guard planes by copy engines
 hidden = 1 - (t_overlap - t_no_comm) / (t_serial - t_no_comm), times = device loop time per iteration, max over ranks.
 Optional extra variants: --p2p (PPS_HALO_P2P=1: CUDA-IPC peer pushes on copy engines, with the 3-stream schedule and with the
 single-launch in-kernel wait PPS_OVERLAP=3), --inkernel (PPS_OVERLAP=2).
@@ -37,15 +38,16 @@ def main():
     D = bench.Dist(rank, world, "cuda")
     X, B = bench.manufactured_slab(npglobal, world, rank)
     out = {"npglobal": npglobal, "world": world, "iters": iters}
-    variants = [("no_comm", {"PPS_DEBUG_NO_HALO": "1", "PPS_OVERLAP": "0", "PPS_HALO_P2P": "0"}),
-                ("serial", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "0", "PPS_HALO_P2P": "0"}),
-                ("overlap", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "1", "PPS_HALO_P2P": "0"})]
+    base = {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "1", "PPS_HALO_P2P": "1", "PPS_ALLREDUCE_P2P": "0"}
+    variants = [("no_comm", dict(base, PPS_DEBUG_NO_HALO="1", PPS_OVERLAP="0", PPS_HALO_P2P="0")),
+                ("serial", dict(base, PPS_OVERLAP="0", PPS_HALO_P2P="0")),
+                ("overlap", dict(base, PPS_HALO_P2P="0")),       # three streams, faces over NCCL send/recv
+                ("p2p", dict(base))]                              # three streams, faces pushed by the copy engines (the default)
     if "--p2p" in sys.argv:
-        variants.append(("p2p", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "1", "PPS_HALO_P2P": "1"}))
-    if "--p2p" in sys.argv:
-        variants.append(("p2p_inkernel", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "3", "PPS_HALO_P2P": "1"}))
+        variants.append(("p2p_inkernel", dict(base, PPS_OVERLAP="3")))
+        variants.append(("p2p_arp2p", dict(base, PPS_ALLREDUCE_P2P="1")))
     if "--inkernel" in sys.argv:
-        variants.append(("inkernel", {"PPS_DEBUG_NO_HALO": "0", "PPS_OVERLAP": "2", "PPS_HALO_P2P": "0"}))
+        variants.append(("inkernel", dict(base, PPS_OVERLAP="2", PPS_HALO_P2P="0")))
     for name, env in variants:
         os.environ.update(env)
         uid = D.bcast_bytes(pps.get_unique_id() if rank == 0 else None, 128)
@@ -67,7 +69,7 @@ def main():
     out["exposed_comm_ms_serial"] = tsr - tn
     out["exposed_comm_ms_overlap"] = to - tn
     out["hidden_fraction"] = 1 - (to - tn) / (tsr - tn) if tsr > tn else None
-    for extra in ("p2p", "inkernel"):
+    for extra in ("p2p", "p2p_inkernel", "p2p_arp2p", "inkernel"):
         if extra + "_ms_per_iter" in out:
             out["hidden_fraction_" + extra] = 1 - (out[extra + "_ms_per_iter"] - tn) / (tsr - tn) if tsr > tn else None
     if rank == 0:

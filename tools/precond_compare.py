@@ -32,25 +32,39 @@ def main():
     npglobal = (n, n, n)
     X, B = bench.manufactured_slab(npglobal, world, rank)
     out = {"npglobal": npglobal, "layout": [1, 1, world]}
-    for name, pre in (("unpreconditioned", pps.PRECOND_NONE), ("chebyshev11_block_jacobi", pps.PRECOND_CHEBYSHEV)):
+    variants = [("unpreconditioned", dict(precond=pps.PRECOND_NONE)),
+                ("chebyshev11_block_jacobi", dict(precond=pps.PRECOND_CHEBYSHEV, cheb_block=0)),                   # one kernel per sweep: 280 B/cell per call
+                ("chebyshev11_block_jacobi_blocked3", dict(precond=pps.PRECOND_CHEBYSHEV, cheb_block=3)),          # 3 sweeps per HBM pass: 96 B/cell per call
+                ("chebyshev11_block_jacobi_blocked3_fp32", dict(precond=pps.PRECOND_CHEBYSHEV, cheb_block=3, cheb_precision=pps.CHEB_FP32)),
+                ("chebyshev11_block_jacobi_blocked4_fp32", dict(precond=pps.PRECOND_CHEBYSHEV, cheb_block=4, cheb_precision=pps.CHEB_FP32)),
+                ("chebyshev11_local_eig_blocked3", dict(precond=pps.PRECOND_CHEBYSHEV, cheb_block=3, cheb_eigenvalues=pps.CHEB_EIG_LOCAL)),
+                ("chebyshev11_global_comm", dict(precond=pps.PRECOND_CHEBYSHEV, precond_communication=1))]
+    if "--quick" in sys.argv:
+        variants = variants[:3] + variants[3:4]
+    for name, kw in variants:
         uid = D.bcast_bytes(pps.get_unique_id() if rank == 0 else None, 128) if world > 1 else None
-        s = pps.PoissonSolver(pps.make_config(npglobal, nranks=(1, 1, world), bcs=(0,) * 6, precond=pre, tolerance=1e-8, max_iter=6000,
-                                              device=local), rank=rank, world_size=world, unique_id=uid)
+        s = pps.PoissonSolver(pps.make_config(npglobal, nranks=(1, 1, world), bcs=(0,) * 6, tolerance=1e-8, max_iter=6000, device=local, **kw),
+                              rank=rank, world_size=world, unique_id=uid)
         my = rank if world > 1 else 0
         s.set_fields(my, X, B)
         s.save_fields()
-        s.solve()                      # warm-up
+        s.set_max_iterations(30)
+        s.solve()                      # warm-up: 30 iterations of the same loop
+        s.set_max_iterations(6000)
         s.restore_fields()
         D.barrier()
         s.solve()
         D.barrier()
         secs = D.max(s.solver_seconds)
-        out[name] = dict(iterations=s.iterations, seconds=secs, true_residual=s.error_operator,
-                         mlups=n ** 3 * s.iterations / secs / 1e6, operator_applies_per_iteration=2 if pre == pps.PRECOND_NONE else 2 + 2 * 9)
+        out[name] = dict(iterations=s.iterations, seconds=secs, ms_per_iteration=D.max(s.loop_seconds) / max(1, s.iterations) * 1e3,
+                         true_residual=s.error_operator, mlups=n ** 3 * s.iterations / secs / 1e6, launches=s.launch_count)
+        if rank == 0:
+            print("#", name, json.dumps(out[name]), file=sys.stderr, flush=True)
         s.close()
-    a, b = out["unpreconditioned"], out["chebyshev11_block_jacobi"]
-    out["iteration_ratio"] = a["iterations"] / b["iterations"]
-    out["time_ratio_unpreconditioned_over_preconditioned"] = a["seconds"] / b["seconds"]
+    a = out["unpreconditioned"]
+    for name, _ in variants[1:]:
+        out[name]["iteration_ratio_vs_unpreconditioned"] = a["iterations"] / out[name]["iterations"]
+        out[name]["speedup_vs_unpreconditioned"] = a["seconds"] / out[name]["seconds"]
     if "--oracle" in sys.argv and rank == 0:
         from oracle import pyoracle as po
         for name, pre in (("unpreconditioned", po.PRECOND_NONE), ("chebyshev11_block_jacobi", po.PRECOND_CHEBYSHEV)):
