@@ -1976,7 +1976,13 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
     // peer-memory face transport for z-slabs (copy engines + DMA-written epoch flags, no SM, no NCCL kernel): the default since
     // round 2 (2 GPUs, 1024x1024x256: 90 % of the exchange hidden against 76 % over NCCL); PPS_HALO_P2P=0 forces NCCL send/recv
     if (world > 1 && env_int("PPS_HALO_P2P", 1) && h->overlap) setup_p2p(h.get());
-    if (world > 1 && world <= 256 && env_int("PPS_ALLREDUCE_P2P", 0)) setup_allreduce_p2p(h.get());
+    // In-kernel allreduce over peer memory (PeerReduce): EXPERIMENTAL.  Parity-green on 2 GPUs (tests/test_gpu_multi.py), worth
+    // +0.2 % there; on 8 GPUs it produced wrong sums (bench.py's parity gate against the reference's first 20 iterations failed with
+    // 1.5e-3 at iteration 10; not root-caused) -- so it is refused beyond 2 ranks unless forced with PPS_ALLREDUCE_P2P=2 for debugging.
+    const int ar_mode = env_int("PPS_ALLREDUCE_P2P", 0);
+    if (world > 1 && world <= 256 && (ar_mode == 2 || (ar_mode == 1 && world <= 2))) setup_allreduce_p2p(h.get());
+    else if (ar_mode == 1 && world > 2 && rank == 0)
+        std::fprintf(stderr, "[pps] PPS_ALLREDUCE_P2P=1 ignored on %d ranks (validated on 2 only): NCCL allreduce\n", world);
     h->ctl_host = Ctl{};
     h->ctl_host.norm_b = 1;
     upload_ctl(h.get());
