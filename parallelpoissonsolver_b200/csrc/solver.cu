@@ -106,6 +106,8 @@ struct pps_handle {
     int by = 8;                 // tile rows of the plain-load kernels
     int stencil_impl = 1;       // 0 plain loads, 1 TMA ring (stencil_tma.cuh)
     int by_tma = 8;             // tile rows of the TMA operator kernels (8 or 16)
+    int by_hint = 0;            // tile rows of the operator kernel whose tiling is being made, 0 = by_tma (PPS_FUSE_BY_S: fused_s sweep)
+    int fuse_by_s = 16;
     int zchunk_hint = 0;        // z-chunk of the operator kernel whose tiling is being made, 0 = default (see make_tiling)
     int tma_l2_promo = 3;       // PPS_TMA_L2PROMO: 0 none, 1 64 B, 2 128 B, 3 256 B (tuning sweeps)
     int zchunk_fused_p = 0, zchunk_fused_s = 0;   // PPS_ZCHUNK_FUSED_P / _S: z-chunk of the two fused kernels (0 = the operator kernels' value)
@@ -282,7 +284,7 @@ struct Tiling {
 static Tiling make_tiling(const pps_handle* h, const BlockGeom& g, const Box& box, bool stencil) {
     Tiling t;
     const bool tma = stencil && h->stencil_impl == 1;
-    const int by = tma ? h->by_tma : h->by;
+    const int by = tma ? (h->by_hint > 0 ? h->by_hint : h->by_tma) : h->by;
     t.block = dim3(32, tma ? by + 1 : by, 1);
     const int bx0 = (std::max(box.i0, 1) - 1) / 64, bx1 = (std::min(box.i1, g.n[0] + 1) - 2) / 64 + 1;
     const int by0 = (std::max(box.j0, 1) - 1) / by, by1 = (std::min(box.j1, g.n[1] + 1) - 2) / by + 1;
@@ -305,6 +307,11 @@ static Tiling make_tiling(const pps_handle* h, const BlockGeom& g, const Box& bo
         }
     }
     zc = std::min(zc, nzb);
+    if (stencil) {
+        // balanced chunks: never a sliver at the end (a 1-plane chunk still streams 3 planes)
+        const int nch = (nzb + zc - 1) / zc;
+        zc = (nzb + nch - 1) / nch;
+    }
     t.zchunk = zc;
     t.grid = dim3(gx, gy, (nzb + zc - 1) / zc);
     t.org = TileOrigin{bx0, by0, box.k0};
@@ -1514,13 +1521,17 @@ static void bicgstab_iteration_fused(pps_handle* h) {
     if (h->fuse_s) {
         {   // s = r - alpha v ; t = A s ; sum s.t, t.t ; omega                        :168-225
             const FieldSet in = (first || !h->fuse_p) ? FieldSet(sel_v, sel_r) : FieldSet(sel_v);
+            h->by_hint = (!parity && h->fuse_by_s == 16) ? 16 : 0;
             overlapped_operator(h, in, in, 2, OP_BICG_OMEGA, false, 1, [&](Block& b, const Box& box, const Tiling& t, const RedCtx& red) {
                 if (parity) launch_tma_pre<8, 6, true>(h, KC_FUSED_S, b, box, PreSUpdate<true>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
+                else if (h->by_hint == 16 && h->fuse_stages_s == 3) launch_tma_pre<16, 3, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
+                else if (h->by_hint == 16) launch_tma_pre<16, 4, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
                 else if (h->fuse_stages_s == 3) launch_tma_pre<8, 3, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
                 else if (h->fuse_stages_s == 4) launch_tma_pre<8, 4, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
                 else        launch_tma_pre<8, 6, false>(h, KC_FUSED_S, b, box, PreSUpdate<false>{b.s, b.r, b.v, 0}, EpiStoreDot2Self{b.t}, red, t, true);
             });
         }
+        h->by_hint = 0;
         if (h->fuse_check && !h->fuse_p) {
             Block& b = h->blocks[0];
             const Box box = b.g.solver_box();
@@ -1858,6 +1869,7 @@ static pps_handle* create(const pps_config& cfg, int rank, int world, const unsi
         h->fuse_p = env_int("PPS_FUSE_P", 1) != 0;
         h->fuse_s = env_int("PPS_FUSE_S", 1) != 0;
         h->fuse_check = env_int("PPS_FUSE_CHECK", 0);
+        h->fuse_by_s = env_int("PPS_FUSE_BY_S", 16);   // 64 x 16 tiles for fused_s (halo rows 18/16 instead of 10/8): 0.753 ms against 0.771 ms at 512^3
         h->fuse_stages_p = env_int("PPS_FUSE_STAGES_P", 3);   // 3 stages = 64 KB of ring = 3 CTAs per SM: 1.062 ms against 1.106 ms with 4 stages at 512^3
         h->fuse_stages_s = env_int("PPS_FUSE_STAGES_S", 4);   // 46 KB of ring = 4 CTAs per SM: 0.789 ms against 0.799 ms with 6 stages at 512^3
     }

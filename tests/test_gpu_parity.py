@@ -431,6 +431,7 @@ def test_fused_schedule_is_bitwise_identical_to_split(np_, nranks, bcs, arith, m
     pps = _pps()
     # same z-chunks for every operator kernel (the default picks them per kernel from its occupancy), hence the same reduction tree
     monkeypatch.setenv("PPS_ZCHUNK_STENCIL", "8")
+    monkeypatch.setenv("PPS_FUSE_BY_S", "8")          # and the same 64 x 8 tiles (the default gives fused_s 64 x 16 tiles)
     a = pps.ARITH_PARITY if arith == "parity" else pps.ARITH_FAST
     o, s_split = _pair(np_, nranks=nranks, bcs=bcs, arithmetic=a, fusion=pps.FUSE_SPLIT)
     o.set_problem()
@@ -459,6 +460,7 @@ def test_fused_schedule_repeat_solves_are_reproducible(monkeypatch):
     solve: three solves on one handle must agree with each other and with the split schedule to the last bit."""
     pps = _pps()
     monkeypatch.setenv("PPS_ZCHUNK_STENCIL", "32")   # one reduction tree for both schedules
+    monkeypatch.setenv("PPS_FUSE_BY_S", "8")
     n = 256
     o, s_split = _pair((n, n, n), max_iter=3000, fusion=pps.FUSE_SPLIT)
     o.set_problem()

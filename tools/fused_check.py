@@ -13,6 +13,9 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# one reduction tree for both schedules: the defaults pick z-chunks and tile heights per kernel
+os.environ.setdefault("PPS_ZCHUNK_STENCIL", "32")
+os.environ.setdefault("PPS_FUSE_BY_S", "8")
 import parallelpoissonsolver_b200 as pps  # noqa: E402
 from tools.probe import manufactured  # noqa: E402
 

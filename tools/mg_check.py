@@ -63,6 +63,7 @@ def main():
 
     if "fusecmp" in flags:
         os.environ["PPS_ZCHUNK_STENCIL"] = "8"   # one reduction tree for both schedules (the default picks z-chunks per kernel)
+        os.environ["PPS_FUSE_BY_S"] = "8"        # ... and tile heights
     s, x = solve_with(pps.FUSE_AUTO)
     fused_equals_split = None
     if "fusecmp" in flags:
