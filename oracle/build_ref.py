@@ -183,7 +183,7 @@ def build_dropin(name, force=False):
     return exe
 
 
-DROPIN_CONFIGS = ["default", "d64", "m24_cheb", "cg32"]
+DROPIN_CONFIGS = ["default", "d64", "m24_cheb", "cg32", "nb24", "nc24", "chm24", "o1cgm24", "q24_cheb", "l48", "m24_chebg"]
 
 
 def build_one(name, shim_obj, force=False):

@@ -22,6 +22,7 @@ STACKS = {
     "o1cgm24": "BaseCG, orderNeumanBcs = 1",
     "q24_cheb": "DIM = 2, BiCGSTAB + Chebyshev",
     "l48": "DIM = 1, BiCGSTAB",
+    "m24_chebg": "BiCGSTAB + ChebyshevIteration<.., communicationON, ..> in the preconditioner slot (global polynomial preconditioner)",
 }
 
 
