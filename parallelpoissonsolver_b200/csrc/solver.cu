@@ -82,6 +82,7 @@ struct Block {
     double *mp = nullptr, *z = nullptr;              // alias p / r without a preconditioner (noneSolver.hpp:24-27)
     double *cy = nullptr, *cz = nullptr, *cw = nullptr;
     double *c4 = nullptr;                            // fourth iterate buffer of the temporally blocked Chebyshev schedule
+    double *check_buf = nullptr;                     // per-CTA partial sums / maxima of pps_check_solution
     double theta = 0, delta = 0, sigma = 0;          // Chebyshev constants of the PRECONDITIONER on this block (global, or the block's own)
     double *x_saved = nullptr, *b_saved = nullptr;
     double *p2 = nullptr, *v2 = nullptr, *s = nullptr;   // PPS_FUSE_FULL: ping-pong p / v, separate s
@@ -2025,6 +2026,7 @@ static void destroy(pps_handle* h) {
     for (auto& b : h->blocks) {
         for (double* p : b.owned) cudaFree(p);
         if (b.ictl) cudaFree(b.ictl);
+        if (b.check_buf) cudaFree(b.check_buf);
         if (b.ihist_host) cudaFreeHost(b.ihist_host);
     }
     for (auto e : h->inner_events)
@@ -2082,6 +2084,36 @@ struct OpFillHash {
         st2(out + idx, make_double2(val(idx), val(idx + 1)), m0, m1);
     }
 };
+
+// per-CTA sum and max of |x - u| over the data range (rows are grid-strided, columns block-strided); max starts at -1 like the
+// reference's (iterativeSolverBase.hpp:298)
+__global__ void check_solution_kernel(const double* __restrict__ x, const double* __restrict__ u, Dims d, Box bx, double* __restrict__ psum,
+                                      double* __restrict__ pmax) {
+    const int nj = bx.j1 - bx.j0;
+    const long long rows = static_cast<long long>(nj) * (bx.k1 - bx.k0);
+    double s = 0.0, m = -1.0;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int j = bx.j0 + static_cast<int>(row % nj), k = bx.k0 + static_cast<int>(row / nj);
+        const long long base = kOff + d.pitch * (j + static_cast<long long>(d.ny + 2) * k);
+        for (int i = bx.i0 + threadIdx.x; i < bx.i1; i += blockDim.x) {
+            const double e = fabs(x[base + i] - u[base + i]);
+            s += e;
+            m = fmax(m, e);
+        }
+    }
+    __shared__ double ss[8], sm[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(kFullMask, s, o);
+        m = fmax(m, __shfl_down_sync(kFullMask, m, o));
+    }
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sm[threadIdx.x >> 5] = m; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { s += ss[w]; m = fmax(m, sm[w]); }
+        psum[blockIdx.x] = s;
+        pmax[blockIdx.x] = m;
+    }
+}
 
 // out[0] += number of differing entries, out[1] = min index of a differing entry
 __global__ void compare_bits_kernel(const double* __restrict__ a, const double* __restrict__ b, long long n, unsigned long long* out) {
@@ -2386,20 +2418,23 @@ int pps_check_solution(pps_handle* h, int rank, const double* u_exact_host, doub
     if (h->operator_only) throw std::runtime_error("pps_check_solution: handle is operator-only (PPS_FLAG_OPERATOR_ONLY)");
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
     Block* b = find_block(h, rank);
-    std::vector<double> x(static_cast<size_t>(b->g.ref_total()));
-    download_field(h, *b, x.data(), b->x);
+    // checkSolutionLocalGlobal (iterativeSolverBase.hpp:300-317): sum and max of |x - u| over the data range, reporting only.
+    // u goes up (t is a free work vector between solves), per-CTA partial sums / maxima come back and are combined in index order.
+    constexpr int kBlocks = 148 * 8;
+    // (the buffer is per BLOCK: with virtual ranks the rank-threads of the C++ driver call this concurrently on one handle, each for its own block)
+    if (!b->check_buf) PPS_CUDA_CHECK(cudaMalloc(&b->check_buf, sizeof(double) * 2 * kBlocks));
+    upload_field(h, *b, b->t, u_exact_host);
+    pps::check_solution_kernel<<<kBlocks, 256, 0, h->stream>>>(b->x, b->t, b->g.dims, b->g.data_box(), b->check_buf, b->check_buf + kBlocks);
+    check_launch("check_solution");
+    std::vector<double> part(2 * kBlocks);
+    PPS_CUDA_CHECK(cudaMemcpyAsync(part.data(), b->check_buf, sizeof(double) * 2 * kBlocks, cudaMemcpyDeviceToHost, h->stream));
+    zero_field(h, *b, b->t);
     PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    // checkSolutionLocalGlobal (iterativeSolverBase.hpp:300-317): data range, reporting only
-    const long long sj = b->g.ref_extent(0), sk = sj * b->g.ref_extent(1);
-    const int j0 = b->g.dim >= 2 ? 1 : 0, k0 = b->g.dim >= 3 ? 1 : 0;   // unused axes: the single point is index 0
     double s = 0, m = -1;
-    for (int k = k0; k < k0 + b->g.n[2]; k++)
-        for (int j = j0; j < j0 + b->g.n[1]; j++)
-            for (int i = 1; i <= b->g.n[0]; i++) {
-                const double e = std::abs(x[i + sj * j + sk * k] - u_exact_host[i + sj * j + sk * k]);
-                s += e;
-                if (e > m) m = e;
-            }
+    for (int q = 0; q < kBlocks; q++) {
+        s += part[q];
+        if (part[kBlocks + q] > m) m = part[kBlocks + q];
+    }
     *sum_abs = s;
     *max_abs = m;
     PPS_API_END

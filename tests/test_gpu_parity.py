@@ -520,3 +520,29 @@ def test_graph_replay_is_bitwise_identical(monkeypatch, solver, precond):
         s.close(); o.close()
     assert np.array_equal(res["0"][0], res["1"][0]) and np.array_equal(res["0"][1], res["1"][1])
     assert res["0"][2] == res["1"][2]
+
+
+@pytest.mark.parametrize("np_,nranks,bcs,dim", [((40, 24, 32), (1, 1, 2), (0, 1, 0, 1, 0, 0), 3), ((67, 9, 5), (1, 1, 1), (1, 0, 1, 0, 0, 1), 3),
+                                                ((24, 20, 1), (2, 1, 1), (0, 1, 0, 1, 0, 0), 2)])
+def test_check_solution_matches_numpy(np_, nranks, bcs, dim):
+    """pps_check_solution (checkSolutionLocalGlobal, iterativeSolverBase.hpp:283-408) reduces |x - u| on the device: sum and max over the
+    data range of every block must equal numpy's on the downloaded solution"""
+    pps = _pps()
+    ocfg = po.make_config(np_, nranks, bcs=bcs, dim=dim)
+    o = po.Oracle(ocfg)
+    o.set_problem()
+    s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg))
+    H.hand_over_problem(o, s)
+    s.solve()
+    rng = np.random.default_rng(2)
+    for r in range(o.world):
+        x = s.get_solution(r)
+        u = rng.standard_normal(x.shape)
+        bi = o.block(r)
+        ld = bi.limits_data
+        box = (slice(ld[4], ld[5]), slice(ld[2], ld[3]), slice(ld[0], ld[1]))
+        want_sum, want_max = np.abs(x[box] - u[box]).sum(), np.abs(x[box] - u[box]).max()
+        got_sum, got_max = s.check_solution(r, u)
+        assert got_max == want_max
+        assert abs(got_sum - want_sum) <= 1e-12 * want_sum
+    s.close(); o.close()
