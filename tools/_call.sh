@@ -1,5 +1,6 @@
-O=gpurun_out/c17
+O=gpurun_out/c18
 mkdir -p $O
-timeout 1500 python -m pytest tests -m gpu -q -x > $O/gpu_suite.log 2>&1
-tail -6 $O/gpu_suite.log | cut -c1-400
-timeout 100 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -2 $O/smoke.log | cut -c1-200
+PPS_CHEB_BLOCK=3 timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:cheb_blocked_kernel -s 40 -c 1 -f -o $O/prof_r02_256_cheb_blocked3 python tools/probe.py solve 256 cheb > $O/ncu_blocked.log 2>&1
+PPS_CHEB_BLOCK=3 PPS_CHEB_F32=1 timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:cheb_blocked_kernel -s 40 -c 1 -f -o $O/prof_r02_256_cheb_blocked3_f32 python tools/probe.py solve 256 cheb > $O/ncu_blocked_f32.log 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:EpiChebStep -s 40 -c 1 -f -o $O/prof_r02_256_cheb_step python tools/probe.py solve 256 cheb > $O/ncu_step.log 2>&1
+ls -la $O | head

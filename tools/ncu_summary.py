@@ -12,11 +12,13 @@ import sys
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "l1tex__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
-        "sm__cycles_elapsed.max", "smsp__cycles_active.avg"]
+        "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_elapsed", "lts__t_sector_hit_rate.pct",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor"]
 
 
 def short(name):
-    m = re.search(r"(stencil_tma_pre_kernel|stencil_tma_kernel|stencil_kernel|pointwise_kernel)<([^>]*(?:<[^>]*>)?[^>]*)>", name)
+    m = re.search(r"(cheb_blocked_kernel|stencil_tma_pre_kernel|stencil_tma_kernel|stencil_kernel|pointwise_kernel)<([^>]*(?:<[^>]*>)?[^>]*)>", name)
     if m:
         return m.group(1) + "<" + m.group(2) + ">"
     return name.split("(")[0][:60]
