@@ -29,6 +29,9 @@
 namespace pps {
 
 constexpr int kChebMaxLev = 4;
+#ifndef PPS_CHEB_OCC2_MAXLEV
+#define PPS_CHEB_OCC2_MAXLEV 0   // fp64: depths up to this value are compiled for two CTAs per SM (64 registers spill the fp64 windows: 0 = none)
+#endif
 
 template <typename T> struct ChebVec;
 template <> struct ChebVec<double> { using type = double2; };
@@ -148,8 +151,12 @@ struct ChebIO {
 // ------------------------------------------------------------------------------------------------
 template <int N> struct ChebInt { static constexpr int value = N; };
 
+// two CTAs per SM (<= 64 registers) where the register windows allow it: the kernel is latency bound at 16 warps per SM
+template <int NLEV, class Form>
+struct ChebOcc { static constexpr int kMinBlocks = (sizeof(typename Form::T) == 4 || NLEV <= PPS_CHEB_OCC2_MAXLEV) ? 2 : 1; };
+
 template <int NLEV, int FY, bool FIRST, bool LAST, class Form>
-__global__ void __launch_bounds__(32 * FY) cheb_blocked_kernel(Dims d, Box rg, ChebTile tl, Form fm, ChebIO<typename Form::T> io,
+__global__ void __launch_bounds__(32 * FY, ChebOcc<NLEV, Form>::kMinBlocks) cheb_blocked_kernel(Dims d, Box rg, ChebTile tl, Form fm, ChebIO<typename Form::T> io,
                                                               const Ctl* ctl) {
     if (ctl != nullptr && ctl->done) return;
     using T = typename Form::T;
