@@ -11,6 +11,8 @@
  * (grep -oh "MPI_[A-Za-z_]*" over solverPoissonMPI_CPU/):
  *   Init Finalize Comm_size Comm_rank Barrier Allreduce Reduce Bcast
  *   Isend Irecv Waitall Type_indexed Type_commit
+ * plus the four MPI-IO calls of the alpaka tree's main.cpp (solverPoissonMPI_alpaka/src/main.cpp:137-145:
+ * File_open / File_seek / File_write / File_close with an individual file pointer per rank).
  * Semantics: sends are eager and buffered (the reference never waits on its
  * send requests, communicationMPI.hpp:306-316), matching is FIFO per (src,dst),
  * reductions sum in rank order 0..n-1 on every rank (deterministic).
@@ -62,6 +64,20 @@ int MPI_Waitall(int count, MPI_Request* reqs, MPI_Status* statuses);
 int MPI_Type_indexed(int count, const int* blocklens, const int* displs, MPI_Datatype oldtype, MPI_Datatype* newtype);
 int MPI_Type_commit(MPI_Datatype* type);
 int MPI_Type_free(MPI_Datatype* type);
+
+/* MPI-IO subset: every rank owns a descriptor and an individual file pointer (positional writes) */
+typedef struct pps_shim_file* MPI_File;
+typedef long long MPI_Offset;
+typedef int MPI_Info;
+#define MPI_INFO_NULL 0
+#define MPI_MODE_CREATE 1
+#define MPI_MODE_WRONLY 4
+#define MPI_MODE_RDONLY 2
+#define MPI_SEEK_SET 600
+int MPI_File_open(MPI_Comm comm, const char* filename, int amode, MPI_Info info, MPI_File* fh);
+int MPI_File_seek(MPI_File fh, MPI_Offset offset, int whence);
+int MPI_File_write(MPI_File fh, const void* buf, int count, MPI_Datatype type, MPI_Status* status);
+int MPI_File_close(MPI_File* fh);
 
 /* launcher side (not part of MPI): run `fn(argc, argv)` on `world` rank-threads */
 int pps_shim_run(int world, int (*fn)(int, char**), int argc, char** argv);

@@ -14,6 +14,9 @@
 #include <unordered_map>
 #include <vector>
 
+#include <fcntl.h>
+#include <unistd.h>
+
 namespace {
 
 struct IndexedType {
@@ -316,5 +319,44 @@ int MPI_Type_indexed(int count, const int* blocklens, const int* displs, MPI_Dat
 
 int MPI_Type_commit(MPI_Datatype*) { return MPI_SUCCESS; }
 int MPI_Type_free(MPI_Datatype* t) { if (t) *t = MPI_DATATYPE_NULL; return MPI_SUCCESS; }
+
+// MPI-IO subset (alpaka tree, src/main.cpp:137-145): one descriptor + individual file pointer per rank-thread.
+struct pps_shim_file {
+    int fd;
+    long long pos;
+};
+
+int MPI_File_open(MPI_Comm, const char* filename, int amode, MPI_Info, MPI_File* fh) {
+    int flags = (amode & MPI_MODE_WRONLY) ? O_WRONLY : O_RDONLY;
+    if (amode & MPI_MODE_CREATE) flags |= O_CREAT;
+    const int fd = ::open(filename, flags, 0644);
+    if (fd < 0) { *fh = nullptr; return 1; }
+    *fh = new pps_shim_file{fd, 0};
+    barrier();  // collective in MPI: nobody writes before everybody has the file
+    return MPI_SUCCESS;
+}
+int MPI_File_seek(MPI_File fh, MPI_Offset offset, int whence) {
+    if (!fh || whence != MPI_SEEK_SET) return 1;
+    fh->pos = offset;
+    return MPI_SUCCESS;
+}
+int MPI_File_write(MPI_File fh, const void* buf, int count, MPI_Datatype type, MPI_Status*) {
+    if (!fh) return 1;
+    const size_t nbytes = base_size(type) * static_cast<size_t>(count);
+    const char* p = static_cast<const char*>(buf);
+    size_t done = 0;
+    while (done < nbytes) {
+        const ssize_t n = ::pwrite(fh->fd, p + done, nbytes - done, static_cast<off_t>(fh->pos + static_cast<long long>(done)));
+        if (n <= 0) return 1;
+        done += static_cast<size_t>(n);
+    }
+    fh->pos += static_cast<long long>(nbytes);
+    return MPI_SUCCESS;
+}
+int MPI_File_close(MPI_File* fh) {
+    if (fh && *fh) { ::close((*fh)->fd); delete *fh; *fh = nullptr; }
+    barrier();
+    return MPI_SUCCESS;
+}
 
 }  // extern "C"

@@ -462,7 +462,9 @@ static void chebyshev_block(orc_t* o, int rank, double* X, double* Bf) {
  * The alpaka tree's delta has the opposite sign of the CPU tree's (chebyshevIterationAlpaka.hpp:29), hence -B->delta. */
 static void chebyshev_block_alpaka_f32(orc_t* o, int rank, double* X, double* Bf) {
     Block* B = &o->blk[rank];
-    const float theta = (float)B->theta, delta = (float)(-B->delta), sigma = (float)(B->theta / -B->delta);   /* :28-33,67-69,597-599 */
+    /* theta_, delta_ and sigma_ are T_data_chebyshev members (:595-604): theta and delta are evaluated in fp64 and rounded, sigma is the
+     * FLOAT quotient of the two rounded members (:34-35) -- pinned against the unmodified alpaka tree, tests/golden/alp_*.npz */
+    const float theta = (float)B->theta, delta = (float)(-B->delta), sigma = theta / delta;                     /* :28-35,67-76,595-604 */
     float rhoOld = 1 / sigma;                                                                                  /* :123 */
     float rhoCurr = 1 / (2 * sigma - rhoOld);                                                                  /* :124 */
     orc_reset_neumann(o, rank, Bf, 0, 1.0);                                                                    /* :127, on the fp64 field */

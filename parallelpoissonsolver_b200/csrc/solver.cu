@@ -842,7 +842,7 @@ static AlpakaCheb alpaka_cheb_start(const Block& b) {
     const double theta = b.theta, delta = -b.delta;        // b.delta follows the CPU tree (negative)
     a.theta = static_cast<float>(theta);
     a.delta = static_cast<float>(delta);
-    a.sigma = static_cast<float>(theta / delta);
+    a.sigma = a.theta / a.delta;                           // float quotient of the two float members (chebyshevIterationAlpaka.hpp:34-35,595-604)
     a.rho_old = 1 / a.sigma;
     a.rho = 1 / (2 * a.sigma - a.rho_old);
     return a;

@@ -40,6 +40,57 @@ def oracle_config_from_golden(g, nranks=None, max_iter=None, tolerance=None):
         max_iter=int(g["max_iter"]) if max_iter is None else max_iter, cheb_max=int(g["cheb_max"]), **extra)
 
 
+# ---------------------------------------------------------------- fixtures of the reference's alpaka tree (tests/golden/alpaka/)
+ALPAKA_GOLDEN = os.path.join(GOLDEN, "alpaka")
+
+
+def alpaka_golden_names(precond_only=False):
+    names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(ALPAKA_GOLDEN, "*.npz")))
+    return [n for n in names if not (precond_only and n.startswith("alp_none"))]
+
+
+def load_alpaka_golden(name):
+    g = np.load(os.path.join(ALPAKA_GOLDEN, name + ".npz"), allow_pickle=False)
+    return {k: g[k] for k in g.files}
+
+
+def oracle_config_from_alpaka_golden(g):
+    """the alpaka tree's configuration surface (solverPoissonMPI_alpaka/include/inputParam.hpp, solverSetup.hpp): epsilon = 0,
+    T_data_chebyshev and the local / global eigenvalue switch"""
+    return po.make_config(
+        np_=[int(v) for v in g["np"]], nranks=[int(v) for v in g["nranks"]], ds=[float(v) for v in g["ds"]],
+        origin=[float(v) for v in g["origin"]], bcs=[int(v) for v in g["bcs"]],
+        precond=po.PRECOND_CHEBYSHEV if str(g["precond"]) == "cheb" else po.PRECOND_NONE, tolerance=float(g["tolerance"]),
+        max_iter=int(g["max_iter"]), cheb_max=int(g["cheb_max"]), cheb_epsilon=0.0, cheb_rescale_min=float(g["cheb_rescale_min"]),
+        cheb_rescale_max=float(g["cheb_rescale_max"]), cheb_f32=int(g["cheb_f32"]), cheb_eig_local=int(g["cheb_eig_local"]))
+
+
+def alpaka_test_field(gk, gj, gi):
+    """testField() of oracle/ref_dump_alpaka.cpp: exact in fp64, not representable in fp32 (global 0-based data-range indices)"""
+    gi, gj, gk = (np.asarray(a, dtype=np.int64) for a in (gi, gj, gk))
+    h1 = (gi * 73856093 + gj * 19349663 + gk * 83492791) % 4001
+    h2 = (gi * 2654435761 + gj * 40503 + gk * 9973) % 1021
+    return (h1 - 2000) / 4096.0 + h2 / 1099511627776.0
+
+
+def alpaka_precond_case(g, o: po.Oracle):
+    """inputs and expected outputs of the preconditioner fixture `precond_x`: per rank the guard-padded right-hand side (test field
+    on the solver range, zero elsewhere -- what p and r look like), the solver-range box and the reference's X on that box"""
+    B, boxes, want = [], [], []
+    for r in range(o.world):
+        bi = o.block(r)
+        ls, loc, nn = bi.limits_solver, bi.loc, bi.nlocal
+        shp = o.shape(r)
+        k, j, i = np.meshgrid(np.arange(shp[0]), np.arange(shp[1]), np.arange(shp[2]), indexing="ij")
+        f = alpaka_test_field(loc[2] * nn[2] + k - 1, loc[1] * nn[1] + j - 1, loc[0] * nn[0] + i - 1)
+        box = (slice(ls[4], ls[5]), slice(ls[2], ls[3]), slice(ls[0], ls[1]))
+        b = np.zeros(shp)
+        b[box] = f[box]
+        gbox = tuple(slice(loc[d] * nn[d] + s.start - 1, loc[d] * nn[d] + s.stop - 1) for d, s in ((2, box[0]), (1, box[1]), (0, box[2])))
+        B.append(b); boxes.append(box); want.append(np.ascontiguousarray(g["precond_x"][gbox]))
+    return B, boxes, want
+
+
 def assemble_global(fields, blocks, npglobal):
     """per-rank guard-padded arrays -> global data-range array (k, j, i)"""
     out = np.zeros((npglobal[2], npglobal[1], npglobal[0]))

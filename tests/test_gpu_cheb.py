@@ -5,7 +5,8 @@
   arithmetic modes, for every depth (sweeps per HBM pass), with Neumann faces folded in as index remaps and on several blocks;
   in PARITY arithmetic both equal the oracle (= the reference, chebyshevIteration.hpp:48-140) bit for bit.
 * fp32 iterates: PARITY arithmetic reproduces the oracle's restatement of the alpaka kernels (kernelsAlpakaChebyshev.hpp) bit
-  for bit; that restatement itself is unpinned (the alpaka tree cannot be built in this image).
+  for bit, and -- on the fixtures of tests/golden/alpaka/ -- the UNMODIFIED alpaka tree itself (built with its OpenMP CPU accelerator
+  by oracle/build_ref_alpaka.py) bit for bit.
 """
 import numpy as np
 import pytest
@@ -164,6 +165,61 @@ def test_solve_with_alpaka_only_chebyshev_options(f32, local, np_, nranks, bcs):
         assert m10 <= 1e-11 and m20 <= 1e-7
     assert abs(s.iterations - o.iters) <= max(2, o.iters // 6)
     assert s.error_operator < 1.5 * ocfg.tolerance
+    s.close(); o.close()
+
+
+# ---------------------------------------------------------------- the unmodified alpaka tree (tests/golden/alpaka/)
+@pytest.mark.parametrize("name", H.alpaka_golden_names(precond_only=True))
+def test_chebyshev_preconditioner_against_alpaka_golden(name):
+    """ChebyshevIterationAlpaka::operator()(bufX, bufB) of the unmodified alpaka tree (chebyshevIterationAlpaka.hpp:119-310) applied
+    to the fixture's test field: fp32 iterates (T_data_chebyshev = float) to the LAST BIT in PARITY arithmetic at every blocking
+    depth; fp64 iterates to 1e-13 (the alpaka kernels fold the stencil into the recurrence coefficients, the CUDA path follows the
+    CPU tree's expression order); global and block-local eigenvalue bounds, 1-8 blocks."""
+    pps = _pps()
+    g = H.load_alpaka_golden(name)
+    ocfg = H.oracle_config_from_alpaka_golden(g)
+    o = po.Oracle(ocfg)   # geometry only
+    B, boxes, want = H.alpaka_precond_case(g, o)
+    f32 = int(g["cheb_f32"])
+    for depth in ((1, 3) if f32 else (0, 3)):
+        s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, arithmetic=pps.ARITH_PARITY, cheb_block=depth))
+        for r in range(o.world):
+            got = s.apply_preconditioner(r, B[r])[boxes[r]]
+            if f32:
+                assert np.array_equal(got, want[r]), (name, depth, r, float(np.abs(got - want[r]).max()))
+            else:
+                rel = float(np.abs(got - want[r]).max() / np.abs(want[r]).max())
+                H.record_margin("alpaka_golden_fp64_preconditioner", golden=name, depth=depth, rank=r, rel_max=rel)
+                assert rel <= 1e-13, (name, depth, r, rel)
+        s.close()
+    o.close()
+
+
+@pytest.mark.parametrize("name", H.alpaka_golden_names())
+def test_solve_against_alpaka_golden(name):
+    """whole solves of the unmodified alpaka tree (BiCGstabAlpaka + ChebyshevIterationAlpaka, src/main.cpp:83-101): the residual
+    history agrees to rounding through iteration 5 on every fixture and in SURVEY section 7's lock-step (1e-10 @ 10, 1e-7 @ 20; the
+    alpaka tree sums its dot products in yet another order) with fp64 iterates; iteration counts inside the +- 15 % band; true
+    residual below the tolerance.  (fp32 iterates: see test_solve_with_alpaka_only_chebyshev_options for why lock-step ends early.)"""
+    pps = _pps()
+    g = H.load_alpaka_golden(name)
+    ocfg = H.oracle_config_from_alpaka_golden(g)
+    o = po.Oracle(ocfg)
+    o.set_problem()
+    s = pps.PoissonSolver(H.pps_config_from_oracle(ocfg, arithmetic=pps.ARITH_PARITY, cheb_block=3 if int(g["cheb_f32"]) else 0))
+    H.hand_over_problem(o, s)
+    s.solve()
+    hs, hg = s.history(), g["history"]
+    n = min(len(hs), len(hg))
+    rel = np.abs(hs[:n] - hg[:n]) / hg[:n]
+    m5, m10, m20 = float(rel[:6].max()), float(rel[:11].max()), float(rel[:21].max())
+    H.record_margin("alpaka_golden_solve", golden=name, hist_rel_it5=m5, hist_rel_it10=m10, hist_rel_it20=m20, iters=s.iterations,
+                    iters_alpaka=int(g["iters"]), true_residual=s.error_operator)
+    assert s.error_operator < 1.5 * ocfg.tolerance
+    assert abs(s.iterations - int(g["iters"])) <= max(3, 0.15 * int(g["iters"])), (s.iterations, int(g["iters"]))
+    assert m5 <= 1e-11, rel[:6]
+    if not int(g["cheb_f32"]):
+        assert m10 <= 1e-10 and m20 <= 1e-7, (m10, m20)
     s.close(); o.close()
 
 
