@@ -50,11 +50,11 @@ M24 = dict(np=(24, 20, 28), bcs=MIXED, ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 
 
 
 def cfg(np, bcs=DIRICHLET, solver="bicgstab_chebglobal", cheb_type="double", ds=(0.1, 0.1, 0.1), origin=(0, 0, 0),
-        toll_scaling=1e-8, toll_main=1, iter_max=1700, cheb_max=11, rescale_min=500.0, rescale_max=1 - 1e-4):
+        toll_scaling=1e-8, toll_main=1, iter_max=1700, cheb_max=11, rescale_min=500.0, rescale_max=1 - 1e-4, write_files=False):
     # (toll_main stays 1: tollPreconditionerSolver = tollMainSolver * 1e8 must fit an int, solverSetup.hpp:63)
     return dict(np=tuple(np), bcs=tuple(bcs), solver=solver, cheb_type=cheb_type, ds=tuple(ds), origin=tuple(origin),
                 toll_scaling=toll_scaling, toll_main=toll_main, iter_max=iter_max, cheb_max=cheb_max,
-                rescale_min=rescale_min, rescale_max=rescale_max)
+                rescale_min=rescale_min, rescale_max=rescale_max, write_files=write_files)
 
 
 CONFIGS = {
@@ -71,6 +71,8 @@ CONFIGS = {
     # fp64 global: the alpaka kernels' folded 7-point form against the CPU tree's expression order
     "alp_f64_m24": cfg(**M24),
     "alp_none_m24": cfg(solver="bicgstab_none", **M24),
+    # writeResidual / writeSolution = true (inputParam.hpp:46-47): residualHistory.txt and solution.dat from the tree's own main.cpp
+    "alp_files_m24": cfg(write_files=True, **M24),
 }
 
 CXXFLAGS = ["-std=c++17", "-O3", "-DNDEBUG", "-pthread", "-w", "-fopenmp",
@@ -90,6 +92,9 @@ def make_cfg_dir(name, c):
     t = _sub(t, r"> ds=\{[^}]*\}", "> ds={%s}" % ",".join(_fmt(float(v)) for v in c["ds"]), p)
     t = _sub(t, r"origin=\{[^}]*\}", "origin={%s}" % ",".join(_fmt(float(v)) for v in c["origin"]), p)
     t = _sub(t, r"bcsType=\{[^}]*\}", "bcsType={%s}" % ",".join(map(str, c["bcs"])), p)
+    if c.get("write_files"):
+        t = _sub(t, r"writeResidual = false;", "writeResidual = true;", p)
+        t = _sub(t, r"writeSolution = false;", "writeSolution = true;", p)
     open(p, "w").write(t)
     p = os.path.join(dst, "solverSetup.hpp")
     t = open(p).read()

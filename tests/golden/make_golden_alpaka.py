@@ -47,6 +47,32 @@ def alpaka_test_field(gk, gj, gi):
     return (h1 - 2000) / 4096.0 + h2 / 1099511627776.0
 
 
+def run_files_case(name="alp_files_m24", ranks=(1, 1, 2)):
+    """the tree's own main.cpp with writeResidual / writeSolution = true: the two result files as it writes them, next to the
+    full-precision history and the per-rank blocks of the same (deterministic) solve from the dump harness"""
+    c = ba.CONFIGS[name]
+    world = ranks[0] * ranks[1] * ranks[2]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    with tempfile.TemporaryDirectory() as td:
+        r = subprocess.run([os.path.join(ba.OUT, "bin", "alp_solver_" + name), *map(str, ranks)], check=True, capture_output=True, text=True,
+                           env=env, cwd=td)
+        hist_txt = np.frombuffer(open(td + "/residualHistory.txt", "rb").read(), dtype=np.uint8)
+        sol = np.fromfile(td + "/solution.dat")
+        stdout = r.stdout
+    with tempfile.TemporaryDirectory() as td:
+        subprocess.run([os.path.join(ba.OUT, "bin", "alp_dump_" + name), *map(str, ranks), td, "solve"], check=True, capture_output=True, text=True, env=env)
+        s = read_summary(td + "/summary.txt")
+        blocks = np.stack([np.fromfile(f"{td}/rank{q}.x") for q in range(world)])
+        out = dict(residual_history_txt=hist_txt, solution_dat=sol, blocks=blocks, history=np.fromfile(td + "/history.bin"),
+                   iters=int(s["iters"][0]), precond_iters=int(s["precond_iters"][0]), nranks=np.array(ranks), np=np.array(c["np"]),
+                   max_iter=int(c["iter_max"]),
+                   report_labels=np.array([l.split()[0] for l in stdout.splitlines() if l.startswith("timeTot")]))
+    os.makedirs(OUT, exist_ok=True)
+    fn = os.path.join(OUT, "files_%s_%d%d%d.npz" % ((name,) + tuple(ranks)))
+    np.savez_compressed(fn, **out)
+    return fn
+
+
 def run_case(name, ranks):
     c = ba.CONFIGS[name]
     exe = os.path.join(ba.OUT, "bin", "alp_dump_" + name)
@@ -77,8 +103,11 @@ def run_case(name, ranks):
 
 
 if __name__ == "__main__":
-    ba.build(sorted({c[0] for c in CASES}))
+    ba.build(sorted({c[0] for c in CASES} | {"alp_files_m24"}))
     only = set(sys.argv[1:])
+    if not only or "alp_files_m24" in only:
+        fn = run_files_case()
+        print(os.path.basename(fn), os.path.getsize(fn) // 1024, "KiB")
     for name, ranks in CASES:
         if only and name not in only:
             continue

@@ -45,7 +45,7 @@ ALPAKA_GOLDEN = os.path.join(GOLDEN, "alpaka")
 
 
 def alpaka_golden_names(precond_only=False):
-    names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(ALPAKA_GOLDEN, "*.npz")))
+    names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(ALPAKA_GOLDEN, "alp_*.npz")))
     return [n for n in names if not (precond_only and n.startswith("alp_none"))]
 
 

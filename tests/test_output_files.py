@@ -38,6 +38,58 @@ def test_writers(tmp_path):
     assert np.array_equal(sol.reshape(4, 10), np.repeat(np.arange(4) + 0.5, 10).reshape(4, 10))
 
 
+def test_writers_against_the_files_of_the_unmodified_alpaka_tree(tmp_path):
+    """tests/golden/alpaka/files_*.npz holds residualHistory.txt and solution.dat exactly as the reference's alpaka tree wrote them
+    (its own src/main.cpp with writeResidual / writeSolution = true, built by oracle/build_ref_alpaka.py, 1x1x2 ranks) next to the
+    full-precision history and the per-rank blocks of the same solve.  Fed with those numbers, the writers of output.hpp must
+    produce the same bytes (the first line is the solve time: re-emitted from the parsed value)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "alpaka", "files_alp_files_m24_112.npz"))
+    want_txt = bytes(g["residual_history_txt"]).decode()
+    seconds = float(want_txt.split("\n")[0])
+    hist = g["history"]
+    blocks = g["blocks"]
+    ntot = blocks.shape[1]
+    src = tmp_path / "w.cpp"
+    src.write_text(textwrap.dedent('''
+        #include "output.hpp"
+        #include <cstdio>
+        #include <vector>
+        int main() {
+            const double hist[] = {%s};
+            pps_compat::write_residual_history("residualHistory.txt", %s, %d, %d, hist, %d, %d);
+            std::vector<double> blk(%d);
+            FILE* f = std::fopen("blocks.bin", "rb");
+            for (int r = %d - 1; r >= 0; r--) {                       // any order: the offsets are disjoint
+                std::fseek(f, long(sizeof(double)) * %d * r, SEEK_SET);
+                if (std::fread(blk.data(), sizeof(double), blk.size(), f) != blk.size()) return 1;
+                pps_compat::write_solution_block("solution.dat", r, %d, blk.data());
+            }
+            return 0;
+        }
+    ''') % (", ".join(float(v).hex() for v in hist), float(seconds).hex(), int(g["iters"]), int(g["precond_iters"]), len(hist), int(g["max_iter"]),
+            ntot, blocks.shape[0], ntot, ntot))
+    blocks.tofile(tmp_path / "blocks.bin")
+    exe = tmp_path / "w"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include", "reference_compat"), str(src), "-o", str(exe)], check=True)
+    subprocess.run([str(exe)], check=True, cwd=tmp_path, capture_output=True)
+    assert (tmp_path / "residualHistory.txt").read_text() == want_txt
+    # solution.dat: block r at byte offset r * ntot * 8 (src/main.cpp:139-144).  The reference writes fieldX after
+    # checkSolutionLocalGlobal has refreshed its guard cells, the dump harness before: compare the data range.
+    ours = np.fromfile(tmp_path / "solution.dat")
+    assert ours.shape == g["solution_dat"].shape
+    n = [int(v) for v in g["np"]]
+    shp = (blocks.shape[0], n[2] // blocks.shape[0] + 2, n[1] + 2, n[0] + 2)
+    inner = (slice(None), slice(1, -1), slice(1, -1), slice(1, -1))
+    assert np.array_equal(ours.reshape(shp)[inner], g["solution_dat"].reshape(shp)[inner])
+    # the per-phase report of the alpaka driver (solverSetup.hpp:247-268): the aggregate rows the drop-in driver prints too
+    labels = [str(v) for v in g["report_labels"]]
+    assert labels[-6:] == ["timeTotPreconditionerTot", "timeTotCommunicationTot", "timeTotAllReductionTot", "timeTotKernelsBBiCGstabTot",
+                           "timeTotResetNeumanBCs", "timeTotal"]
+    compat = open(os.path.join(ROOT, "include", "reference_compat", "iterativeSolverBase.hpp")).read()
+    for lab in labels[-6:]:
+        assert lab in compat, lab
+
+
 def test_report_lines_match_the_archived_reference_log(tmp_path):
     """include/reference_compat/report.hpp must reproduce the reference's stdout byte for byte: checked against the lines
     of the run the reference archives (solverPoissonMPI_CPU/run/solverScoreP.o:2-8,25,28-31; 4x4x4 ranks, 128x128x256)."""
