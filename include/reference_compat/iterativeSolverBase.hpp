@@ -96,7 +96,7 @@ class SolverAdapter {
         if (self.solver_kind < 0) { std::cerr << "Error: " << name << " is not available as the main solver" << std::endl; std::exit(-1); }
         if (precond.precond_kind < 0) {
             std::cerr << "Error: this preconditioner stack is not implemented on the B200 path (available: NoneSolver, ChebyshevIteration, "
-                         "BiCGSTAB<.., false, communicationOFF, NoneSolver>, BaseCG<.., false, communicationOFF, ChebyshevIteration>)" << std::endl;
+                         "BiCGSTAB<.., false, communicationOFF | communicationON, NoneSolver>, BaseCG<.., false, communicationOFF, ChebyshevIteration>)" << std::endl;
             std::exit(-1);
         }
         if (self.solver_kind == PPS_SOLVER_CHEBYSHEV && precond.precond_kind != PPS_PRECOND_NONE) {
@@ -131,8 +131,10 @@ class SolverAdapter {
         c.cheb_rescale_min = rescaleEigMin;
         c.cheb_rescale_max = rescaleEigMax;
         c.order_neumann = orderNeumanBcs;
-        // communicationON in the preconditioner slot: the Chebyshev sweeps exchange faces (chebyshevIteration.hpp:69-73,97-101)
-        c.precond_communication = (precond.precond_kind == PPS_PRECOND_CHEBYSHEV && precond.communication) ? 1 : 0;
+        // communicationON in the preconditioner slot: the Chebyshev sweeps exchange faces (chebyshevIteration.hpp:69-73,97-101); the nested
+        // BiCGSTAB becomes a global solve (BiCGSTAB.hpp:135-139,156-164,182-186,216-225,247-257 inside the preconditioner)
+        c.precond_communication = ((precond.precond_kind == PPS_PRECOND_CHEBYSHEV || precond.precond_kind == PPS_PRECOND_BICGSTAB_LOCAL) &&
+                                   precond.communication) ? 1 : 0;
         // alpaka-only switches, for a solverSetup.hpp / inputParam.hpp written for that tree:
         //   -DPPS_CHEBYSHEV_FLOAT       T_data_chebyshev = float   (solverPoissonMPI_alpaka/include/solverSetup.hpp:14)
         //   -DPPS_CHEBYSHEV_LOCAL_EIG   `local` eigenvalue bounds  (solverPoissonMPI_alpaka/include/inputParam.hpp:21-22,27)

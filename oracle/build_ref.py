@@ -45,6 +45,10 @@ SOLVER_TYPEDEFS = {
     # GLOBAL Chebyshev preconditioner: the same class with communicationON in the preconditioner slot (chebyshevIteration.hpp:69-73,97-101)
     "bicgstab_chebglobal": "BiCGSTAB<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, "
                            "ChebyshevIteration<DIM, T_data, tollPreconditionerSolver, chebyshevMax, ischebyshevMainLoop, communicationON, T_NoneSolver>>",
+    # GLOBAL nested BiCGSTAB preconditioner: the class of inputParam.hpp:31 with communicationON (face exchanges and allreduces inside the
+    # preconditioner; the alpaka tree names it T_PreconditionerBiCGStabGlobal, solverPoissonMPI_alpaka/include/inputParam.hpp:33)
+    "bicgstab_bicgglob": "BiCGSTAB<DIM, T_data, tollMainSolver, iterMaxMainSolver, isbiCGMainLoop1, communicationON, "
+                         "BiCGSTAB<DIM, T_data, tollPreconditionerSolver, iterMaxPreconditioner, isbiCGMainLoop2, communicationON, T_NoneSolver>>",
     # Chebyshev iteration as the MAIN solver (chebyshevIteration.hpp:61-67,132-139): isMainLoop = true, communicationON
     "cheb_main": "ChebyshevIteration<DIM, T_data, tollMainSolver, chebyshevMax, true, communicationON, T_NoneSolver>",
 }
@@ -54,10 +58,10 @@ MIXED = (0, 1, 0, 1, 0, 1)  # shipped default
 
 
 def cfg(np, bcs=DIRICHLET, solver="bicgstab_none", ds=(0.1, 0.1, 0.1), origin=(0, 0, 0), toll_scaling=1e-10,
-        toll_main=100, iter_max=1700, cheb_max=11, order_neumann=2, rescale_min=None, rescale_max=None, dim=3):
+        toll_main=100, iter_max=1700, cheb_max=11, order_neumann=2, rescale_min=None, rescale_max=None, dim=3, precond_iter_max=None):
     return dict(np=tuple(np), bcs=tuple(bcs), solver=solver, ds=tuple(ds), origin=tuple(origin),
                 toll_scaling=toll_scaling, toll_main=toll_main, iter_max=iter_max, cheb_max=cheb_max,
-                order_neumann=order_neumann, rescale_min=rescale_min, rescale_max=rescale_max, dim=dim)
+                order_neumann=order_neumann, rescale_min=rescale_min, rescale_max=rescale_max, dim=dim, precond_iter_max=precond_iter_max)
 
 
 # name -> configuration.  "default" is the reference exactly as shipped.
@@ -79,6 +83,9 @@ CONFIGS = {
     "cgm24": cfg((24, 20, 28), MIXED, "cg_none", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1)),
     "nb24": cfg((24, 20, 28), MIXED, "bicgstab_bicgloc", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1)),
     "nc24": cfg((24, 20, 28), MIXED, "bicgstab_cgcheb", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1)),
+    "nbg24": cfg((24, 20, 28), MIXED, "bicgstab_bicgglob", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1)),
+    "nbgd32": cfg((32, 32, 32), DIRICHLET, "bicgstab_bicgglob"),
+    "nbg24_i8": cfg((24, 20, 28), MIXED, "bicgstab_bicgglob", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), precond_iter_max=8),
     # first-order Neumann closure (solverSetup.hpp:25 orderNeumanBcs = 1) and Chebyshev as main solver
     "o1m24": cfg((24, 20, 28), MIXED, "bicgstab_none", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), order_neumann=1),
     "o1m24_cheb": cfg((24, 20, 28), MIXED, "bicgstab_cheb", ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), order_neumann=1),
@@ -142,6 +149,8 @@ def make_cfg_dir(name, c):
     t = _sub(t, r"iterMaxMainSolver=[^;]*;", "iterMaxMainSolver=%d;" % c["iter_max"], p)
     t = _sub(t, r"chebyshevMax=[^;]*;", "chebyshevMax=%d;" % c["cheb_max"], p)
     t = _sub(t, r"orderNeumanBcs=[^;]*;", "orderNeumanBcs=%d;" % c.get("order_neumann", 2), p)
+    if c.get("precond_iter_max") is not None:
+        t = _sub(t, r"iterMaxPreconditioner=[^;]*;", "iterMaxPreconditioner=%d;" % c["precond_iter_max"], p)
     if c.get("rescale_min") is not None:
         t = _sub(t, r"rescaleEigMin= [^;]*;", "rescaleEigMin= %s;" % _fmt(float(c["rescale_min"])), p)
     if c.get("rescale_max") is not None:
@@ -183,7 +192,7 @@ def build_dropin(name, force=False):
     return exe
 
 
-DROPIN_CONFIGS = ["default", "d64", "m24_cheb", "cg32", "nb24", "nc24", "chm24", "o1cgm24", "q24_cheb", "l48", "m24_chebg"]
+DROPIN_CONFIGS = ["default", "d64", "m24_cheb", "cg32", "nb24", "nbg24_i8", "nc24", "chm24", "o1cgm24", "q24_cheb", "l48", "m24_chebg"]
 
 
 def build_one(name, shim_obj, force=False):

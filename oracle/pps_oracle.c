@@ -674,8 +674,126 @@ static void chebyshev_all_comm(orc_t* o, double* const* X, double* const* Bf) {
     free(ys);
 }
 
+/* BiCGSTAB<..., isMainLoop = false, communicationON = true, NoneSolver> in the preconditioner slot (BiCGSTAB.hpp:55-322; the alpaka tree's
+ * T_PreconditionerBiCGStabGlobal, solverPoissonMPI_alpaka/include/inputParam.hpp:33): a GLOBAL nested Krylov solve -- face exchanges of
+ * Mp, z and X and rank-ordered allreduces inside the preconditioner, all ranks in lock-step.  Same quirks as the local one: X zeroed (:96),
+ * B divided by its (global) norm and multiplied back (:97,310-314), early return without multiplying back (:118-122). */
+static void global_bicgstab(orc_t* o, double* const* X, double* const* Bf) {
+    const int W = o->world;
+    double* s1 = (double*)calloc((size_t)W, sizeof(double));
+    double* s2 = (double*)calloc((size_t)W, sizeof(double));
+    double** f = (double**)malloc(sizeof(double*) * (size_t)W);
+    for (int r = 0; r < W; r++) {
+        Block* B = &o->blk[r];
+        const size_t nb = sizeof(double) * (size_t)B->ntot;
+        for (int q = 0; q < 7; q++) memset(B->lw[q], 0, nb);                         /* :60-66 */
+        memset(X[r], 0, nb);                                                         /* :96 */
+    }
+    /* normalizeProblemToFieldBNorm<false, true>: iterativeSolverBase.hpp:171-234 (Reduce + Bcast = rank-ordered sum) */
+    for (int r = 0; r < W; r++) {
+        Block* B = &o->blk[r];
+        double s = 0.0;
+        FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; s += Bf[r][q] * Bf[r][q]; }
+        s1[r] = s;
+    }
+    const double nrm = sqrt(rank_sum(o, s1));
+    for (int r = 0; r < W; r++) {
+        Block* B = &o->blk[r];
+        for (long q = 0; q < B->ntot; q++) { X[r][q] /= nrm; Bf[r][q] /= nrm; }
+    }
+    /* computeErrorOperatorA<false, true>: iterativeSolverBase.hpp:236-280 */
+    orc_halo_exchange(o, X);
+    for (int r = 0; r < W; r++) {
+        Block* B = &o->blk[r];
+        double* rk = B->lw[1];
+        orc_reset_neumann(o, r, X[r], 0, 1.0);
+        double s = 0.0;
+        FOR_SOLVER(B, i, j, k) {
+            const long q = i + B->sj * j + B->sk * k;
+            rk[q] = Bf[r][q] - stencil(o, B, X[r], i, j, k);
+            s += rk[q] * rk[q];
+        }
+        s1[r] = s;
+    }
+    const double err0 = sqrt(rank_sum(o, s1));
+    if (err0 < o->c.precond_tolerance) { free(s1); free(s2); free(f); return; }      /* :118-122: returns without de-normalising */
+    for (int r = 0; r < W; r++) {
+        Block* B = &o->blk[r];
+        const size_t nb = sizeof(double) * (size_t)B->ntot;
+        memcpy(B->lw[0], B->lw[1], nb);                                              /* p = r    :125 */
+        memcpy(B->lw[2], B->lw[1], nb);                                              /* r0 = r   :126 */
+    }
+    double alphak = 1, omegak = 1, betak = 1, rho0 = 1, rho1 = 1, err = 0;
+    int iter = 0;
+    (void)betak;
+    while (iter < o->c.precond_max_iter) {
+        for (int r = 0; r < W; r++) { Block* B = &o->blk[r]; memcpy(B->lw[3], B->lw[0], sizeof(double) * (size_t)B->ntot); f[r] = B->lw[3]; }   /* Mp = p (NoneSolver) */
+        orc_halo_exchange(o, f);                                                     /* :135-139 */
+        for (int r = 0; r < W; r++) {
+            Block* B = &o->blk[r];
+            double *r0 = B->lw[2], *Mp = B->lw[3], *AMp = B->lw[4];
+            orc_reset_neumann(o, r, Mp, 0, 1.0);
+            double s = 0.0;
+            FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; AMp[q] = stencil(o, B, Mp, i, j, k); s += r0[q] * AMp[q]; }
+            s2[r] = s;
+        }
+        alphak = rho0 / rank_sum(o, s2);                                             /* :156-160 */
+        for (int r = 0; r < W; r++) {
+            Block* B = &o->blk[r];
+            double *rk = B->lw[1], *AMp = B->lw[4];
+            FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; rk[q] = rk[q] - alphak * AMp[q]; }
+            memcpy(B->lw[5], rk, sizeof(double) * (size_t)B->ntot);                  /* z = r (NoneSolver) */
+            f[r] = B->lw[5];
+        }
+        orc_halo_exchange(o, f);                                                     /* :182-186 */
+        for (int r = 0; r < W; r++) {
+            Block* B = &o->blk[r];
+            double *rk = B->lw[1], *z = B->lw[5], *Az = B->lw[6];
+            orc_reset_neumann(o, r, z, 0, 1.0);
+            FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; Az[q] = stencil(o, B, z, i, j, k); }
+            double a = 0.0, b = 0.0;
+            FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; a += rk[q] * Az[q]; b += Az[q] * Az[q]; }
+            s1[r] = a; s2[r] = b;
+        }
+        omegak = rank_sum(o, s1) / rank_sum(o, s2);                                  /* :216-221 */
+        for (int r = 0; r < W; r++) {
+            Block* B = &o->blk[r];
+            double *rk = B->lw[1], *r0 = B->lw[2], *Mp = B->lw[3], *z = B->lw[5], *Az = B->lw[6];
+            for (long q = 0; q < B->ntot; q++) X[r][q] = X[r][q] + alphak * Mp[q] + omegak * z[q];
+            double a = 0.0, b = 0.0;
+            FOR_SOLVER(B, i, j, k) {
+                const long q = i + B->sj * j + B->sk * k;
+                rk[q] = rk[q] - omegak * Az[q];
+                a += r0[q] * rk[q];
+                b += rk[q] * rk[q];
+            }
+            s1[r] = a; s2[r] = b;
+        }
+        rho1 = rank_sum(o, s1);                                                      /* :247-252 */
+        err = sqrt(rank_sum(o, s2));
+        betak = rho1 / rho0 * alphak / omegak;
+        rho0 = rho1;
+        for (int r = 0; r < W; r++) {
+            Block* B = &o->blk[r];
+            double *p = B->lw[0], *rk = B->lw[1], *AMp = B->lw[4];
+            FOR_SOLVER(B, i, j, k) { const long q = i + B->sj * j + B->sk * k; p[q] = rk[q] + betak * (p[q] - omegak * AMp[q]); }
+        }
+        iter++;
+        if (err < o->c.precond_tolerance) break;
+    }
+    orc_halo_exchange(o, X);                                                         /* :294-298 */
+    for (int r = 0; r < W; r++) {
+        Block* B = &o->blk[r];
+        orc_reset_neumann(o, r, X[r], 0, 1.0);                                       /* :300 */
+        for (long q = 0; q < B->ntot; q++) { X[r][q] *= nrm; Bf[r][q] *= nrm; }      /* :310-314 */
+    }
+    orc_halo_exchange(o, X);                                                         /* :317-321 */
+    free(s1); free(s2); free(f);
+}
+
 void orc_precondition(orc_t* o, double* const* X, double* const* Bf) {
     if (o->c.precond == ORC_PRECOND_CHEBYSHEV && o->c.precond_comm && !o->c.cheb_f32) { chebyshev_all_comm(o, X, Bf); return; }
+    if (o->c.precond == ORC_PRECOND_BICGSTAB_LOCAL && o->c.precond_comm) { global_bicgstab(o, X, Bf); return; }
     for (int r = 0; r < o->world; r++) {
         if (o->c.precond == ORC_PRECOND_CHEBYSHEV && o->c.cheb_f32) chebyshev_block_alpaka_f32(o, r, X[r], Bf[r]);
         else if (o->c.precond == ORC_PRECOND_CHEBYSHEV) chebyshev_block(o, r, X[r], Bf[r]);

@@ -348,8 +348,9 @@ static void finish_reduction(pps_handle* h, int nacc, int op, bool ignore_done) 
         return;
     }
     LaunchScope ls(h, KC_SCALAR);
-    PPS_NCCL_CHECK(nccl().AllReduce(h->ctl->sums, h->ctl->sums, nacc, ncclDouble, ncclSum, h->comm, h->stream));
-    scalar_op_kernel<<<1, 1, 0, h->stream>>>(op, h->ctl, ignore_done ? 1 : 0);
+    // (the active control block: `ctl`, or the nested one inside a GLOBAL nested Krylov preconditioner)
+    PPS_NCCL_CHECK(nccl().AllReduce(h->actl->sums, h->actl->sums, nacc, ncclDouble, ncclSum, h->comm, h->stream));
+    scalar_op_kernel<<<1, 1, 0, h->stream>>>(op, h->actl, ignore_done ? 1 : 0);
     ls.count(1);
 }
 
@@ -1013,7 +1014,7 @@ static bool nested_start(pps_handle* h, Block& b, double* X, double* B, double* 
 
 // launch nested iterations until the (host-mapped) nested history shows convergence `lag` iterations ago
 template <class EnqueueIteration>
-static void nested_iterations(pps_handle* h, Block& b, EnqueueIteration&& enqueue) {
+static void nested_iterations(pps_handle* h, const double* ihist_host, EnqueueIteration&& enqueue) {
     const int lag = std::max(1, h->lag);
     const int nev = static_cast<int>(h->inner_events.size());
     int done_at = h->precond_max_iter;
@@ -1022,7 +1023,7 @@ static void nested_iterations(pps_handle* h, Block& b, EnqueueIteration&& enqueu
         PPS_CUDA_CHECK(cudaEventRecord(h->inner_events[it % nev], h->stream));
         if (it >= lag) {
             PPS_CUDA_CHECK(cudaEventSynchronize(h->inner_events[(it - lag) % nev]));
-            if (b.ihist_host[it - lag + 1] < h->precond_tolerance) { done_at = it - lag + 1; break; }
+            if (ihist_host[it - lag + 1] < h->precond_tolerance) { done_at = it - lag + 1; break; }
         }
     }
     if (done_at == h->precond_max_iter) {
@@ -1030,7 +1031,7 @@ static void nested_iterations(pps_handle* h, Block& b, EnqueueIteration&& enqueu
         // The device stopped at the right iteration (every kernel honours the nested `done`); read the true count for the report.
         PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
         for (int it = std::max(0, h->precond_max_iter - lag); it < h->precond_max_iter; ++it)
-            if (b.ihist_host[it + 1] < h->precond_tolerance) { done_at = it + 1; break; }
+            if (ihist_host[it + 1] < h->precond_tolerance) { done_at = it + 1; break; }
     }
     h->precond_iters += done_at;
 }
@@ -1057,7 +1058,7 @@ static void nested_bicgstab(pps_handle* h, Block& b, double* X, double* B, bool 
     copy_field(h, b, b.ip, b.ir);                                                 // BiCGSTAB.hpp:125-126
     copy_field(h, b, b.ir0, b.ir);
     const bool parity = h->parity;
-    nested_iterations(h, b, [&]() {
+    nested_iterations(h, b.ihist_host, [&]() {
         // Mp = p (NoneSolver) ; ghosts ; v = A Mp ; r0.v ; alpha                                      :133-164
         neumann_ghosts(h, b, b.ip, false, true);
         launch_stencil(h, KC_APPLY_DOT, b, b.ip, box, EpiStoreDot{b.iv, b.ir0}, make_red(h, 1, ts.ctas(), 0, OP_BICG_ALPHA), ts, true);
@@ -1088,7 +1089,7 @@ static void nested_cg_chebyshev(pps_handle* h, Block& b, double* X, double* B, b
     copy_field(h, b, b.ip, b.iz);                                                 // :111
     const bool parity = h->parity;
     const bool order1 = h->cfg.order_neumann == 1;
-    nested_iterations(h, b, [&]() {
+    nested_iterations(h, b.ihist_host, [&]() {
         if (order1) neumann_ghosts(h, b, b.ip, false, true);                      // :123-124
         launch_stencil(h, KC_CG_APPLY, b, b.ip, box, EpiCgApply{b.iv, b.ir, b.iz}, make_red(h, 2, ts.ctas(), 0, OP_CG_ALPHA), ts, true);   // :126-151
         RedCtx none2 = make_red(h, 2, tp.ctas(), 0, OP_NONE);
@@ -1659,9 +1660,128 @@ static void chebyshev_main_sweeps(pps_handle* h) {
     chebyshev_global_sweeps<PAR>(h, sel_t, sel_x);
 }
 
+// ------------------------------------------------------------------------------------------------
+// GLOBAL nested BiCGSTAB preconditioner: BiCGSTAB<.., isMainLoop = false, communicationON = true, NoneSolver> in the preconditioner
+// slot (BiCGSTAB.hpp:55-322; the alpaka tree names it T_PreconditionerBiCGStabGlobal, solverPoissonMPI_alpaka/include/inputParam.hpp:33).
+// The nested solve spans ALL blocks / GPUs: face exchanges of its Mp (= p), z (= r) and X, allreduced scalars -- i.e. the main
+// loop's `fused_operator` machinery (exchange + ghosts + overlapped operator + ticket reduction + allreduce) on the nested work
+// vectors, with ONE nested control block as the active one (block 0's `ictl`: scalars, `done` flag and history on the device; after
+// the allreduce every rank holds the same values, so all ranks take the same host decisions and NCCL calls stay matched).
+// Same quirks as the local one: X zeroed (:96), B divided by its GLOBAL norm and multiplied back (:97,310-314), early return
+// without multiplying back (:118-122), plain-mirror Neumann ghosts.
+// ------------------------------------------------------------------------------------------------
+static double* sel_ip(Block& b) { return b.ip; }
+static double* sel_ir(Block& b) { return b.ir; }
+
+struct GlobalInnerScope {   // the nested control block becomes the active one; reductions stay global
+    pps_handle* h;
+    Ctl* saved;
+    GlobalInnerScope(pps_handle* h_, Ctl* c) : h(h_), saved(h_->actl) { h->actl = c; }
+    ~GlobalInnerScope() { h->actl = saved; }
+};
+
+static void nested_bicgstab_global(pps_handle* h, FieldSel selX, FieldSel selB, bool check_done) {
+    Ctl* gctl = h->blocks[0].ictl;
+    const double* ghist = h->blocks[0].ihist_host;
+    const Ctl* outer = check_done ? h->ctl : nullptr;
+    const bool parity = h->parity;
+    GlobalInnerScope scope(h, gctl);
+    {
+        LaunchScope ls(h, KC_SETUP);
+        inner_begin_kernel<<<1, 1, 0, h->stream>>>(gctl, outer, h->precond_tolerance, h->precond_max_iter);
+        ls.count(1);
+    }
+    for (auto& b : h->blocks) zero_field(h, b, selX(b));                                                    // BiCGSTAB.hpp:96
+    {   // normalizeProblemToFieldBNorm<false, true> (iterativeSolverBase.hpp:171-234): global norm over the solver ranges
+        const unsigned int total = total_ctas(h, false);
+        unsigned int off = 0;
+        for (auto& b : h->blocks) {
+            const Box box = b.g.solver_box();
+            const Tiling t = make_tiling(h, b.g, box, false);
+            launch_pointwise(h, KC_DOT, b, box, OpDot{selB(b), nullptr}, make_red(h, 2, total, off, OP_NORM_B), t, true);
+            off += t.ctas();
+        }
+        finish_reduction(h, 1, OP_NORM_B, false);
+        LaunchScope ls(h, KC_SETUP);
+        for (auto& b : h->blocks) {   // X is all zeros: only B needs the division
+            inner_scale_kernel<<<148 * 8, 256, 0, h->stream>>>(nullptr, selB(b), b.g.dims.total, gctl, outer, 0);
+            ls.count(1);
+        }
+        check_launch("inner_scale");
+    }
+    {   // computeErrorOperatorA<false, true> (:236-280): halo(X), plain-mirror ghosts, r = B - A X, global ||r||
+        halo_exchange(h, FieldSet(selX), true);
+        const unsigned int total = total_ctas(h, true);
+        unsigned int off = 0;
+        for (auto& b : h->blocks) {
+            neumann_ghosts(h, b, selX(b), false, true);
+            const Box box = b.g.solver_box();
+            const Tiling t = make_tiling(h, b.g, box, true);
+            RedCtx red = make_red(h, 1, total, off, OP_RESIDUAL0);
+            if (parity) launch_stencil(h, KC_RESIDUAL, b, selX(b), box, EpiResidual<true>{b.ir, selB(b)}, red, t, true);
+            else        launch_stencil(h, KC_RESIDUAL, b, selX(b), box, EpiResidual<false>{b.ir, selB(b)}, red, t, true);
+            off += t.ctas();
+        }
+        finish_reduction(h, 1, OP_RESIDUAL0, false);
+    }
+    PPS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (ghist[0] < h->precond_tolerance) return;                  // :118-122 (also: the OUTER solve is done, history entry -1)
+    for (auto& b : h->blocks) { copy_field(h, b, b.ip, b.ir); copy_field(h, b, b.ir0, b.ir); }              // :125-126
+    nested_iterations(h, ghist, [&]() {
+        // Mp = p (NoneSolver); halo(Mp); ghosts(Mp); v = A Mp; sum r0.v; alpha                              :133-164
+        fused_operator(h, KC_APPLY_DOT, sel_ip, true, 1, OP_BICG_ALPHA, [](Block& b) { return EpiStoreDot{b.iv, b.ir0}; });
+        for (auto& b : h->blocks) {                                                                          // :168-178
+            const Box box = b.g.solver_box();
+            const Tiling t = make_tiling(h, b.g, box, false);
+            RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
+            if (parity) launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<true>{b.ir, b.iv, 0}, none, t, true);
+            else        launch_pointwise(h, KC_S_UPDATE, b, box, OpSUpdate<false>{b.ir, b.iv, 0}, none, t, true);
+        }
+        // z = r (NoneSolver); halo(z); ghosts(z); t = A z; sum r.t, t.t; omega                               :181-225
+        fused_operator(h, KC_APPLY_DOT2, sel_ir, true, 2, OP_BICG_OMEGA, [](Block& b) { return EpiStoreDot2Self{b.it}; });
+        {
+            const unsigned int total = total_ctas(h, false);
+            unsigned int off = 0;
+            for (auto& b : h->blocks) {                                                                      // :227-246
+                const Box box = b.g.solver_box();
+                const Tiling t = make_tiling(h, b.g, box, false);
+                RedCtx red = make_red(h, 2, total, off, OP_BICG_RHO);
+                if (parity) launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdate<true>{selX(b), b.ir, b.ip, b.ir, b.it, b.ir0, 0, 0}, red, t, true);
+                else        launch_pointwise(h, KC_XR_UPDATE, b, box, OpXRUpdate<false>{selX(b), b.ir, b.ip, b.ir, b.it, b.ir0, 0, 0}, red, t, true);
+                off += t.ctas();
+            }
+            finish_reduction(h, 2, OP_BICG_RHO, false);                                                      // :247-259
+        }
+        for (auto& b : h->blocks) {                                                                          // :262-272
+            const Box box = b.g.solver_box();
+            const Tiling t = make_tiling(h, b.g, box, false);
+            RedCtx none = make_red(h, 0, 1, 0, OP_NONE);
+            if (parity) launch_pointwise(h, KC_P_UPDATE, b, box, OpPUpdate<true>{b.ip, b.ir, b.iv, 0, 0}, none, t, true);
+            else        launch_pointwise(h, KC_P_UPDATE, b, box, OpPUpdate<false>{b.ip, b.ir, b.iv, 0, 0}, none, t, true);
+        }
+    });
+    {
+        // halo(X); ghosts(X) (plain mirrors)                                                                :293-300
+        // these run although the nested solve is `done` by now; only a converged OUTER solve switches them off
+        GlobalInnerScope outer_scope(h, h->ctl);
+        halo_exchange(h, FieldSet(selX), check_done);
+        for (auto& b : h->blocks) neumann_ghosts(h, b, selX(b), false, check_done);
+    }
+    {
+        LaunchScope ls(h, KC_SETUP);                                                                         // :310-314
+        for (auto& b : h->blocks) {
+            inner_scale_kernel<<<148 * 8, 256, 0, h->stream>>>(selX(b), selB(b), b.g.dims.total, gctl, outer, 1);
+            ls.count(1);
+        }
+        check_launch("inner_scale");
+    }
+    halo_exchange(h, FieldSet(selX), check_done);                                                            // :317-321
+}
+
 // X = M(B) on every block: the preconditioner slot of the main solvers
 static void precondition_all(pps_handle* h, FieldSel selX, FieldSel selB, bool check_done) {
     if (h->cfg.precond == PPS_PRECOND_NONE) return;
+    if (h->cfg.precond == PPS_PRECOND_BICGSTAB_LOCAL && h->precond_comm) { nested_bicgstab_global(h, selX, selB, check_done); return; }
     if (h->cfg.precond == PPS_PRECOND_CHEBYSHEV && h->precond_comm) {
         // ChebyshevIteration<.., isMainLoop = false, communicationON, ..> (chebyshevIteration.hpp:69-73,97-101)
         if (h->parity) chebyshev_global_sweeps<true>(h, selB, selX);
@@ -1791,9 +1911,12 @@ static void validate(const pps_config& c, int rank, int world) {
         throw std::runtime_error("chebyshevMax must be >= 3");
     if (c.max_iter < 0) throw std::runtime_error("max_iter must be >= 0");
     if (c.precond_communication != 0 && c.precond_communication != 1) throw std::runtime_error("precond_communication must be 0 or 1");
-    if (c.precond_communication == 1 && (c.precond != PPS_PRECOND_CHEBYSHEV || c.cheb_precision != PPS_CHEB_FP64 || c.cheb_eigenvalues != PPS_CHEB_EIG_GLOBAL))
+    if (c.precond_communication == 1 && c.precond != PPS_PRECOND_BICGSTAB_LOCAL &&
+        (c.precond != PPS_PRECOND_CHEBYSHEV || c.cheb_precision != PPS_CHEB_FP64 || c.cheb_eigenvalues != PPS_CHEB_EIG_GLOBAL))
         throw std::runtime_error("precond_communication = 1 is implemented for the fp64 Chebyshev preconditioner with global eigenvalue bounds "
-                                 "(a global nested BiCGSTAB, alpaka inputParam.hpp:33, is not)");
+                                 "and for the nested BiCGSTAB (BiCGSTAB<.., false, communicationON, NoneSolver>)");
+    if (c.precond_communication == 1 && c.precond == PPS_PRECOND_BICGSTAB_LOCAL && c.solver != PPS_SOLVER_BICGSTAB)
+        throw std::runtime_error("the global nested BiCGSTAB preconditioner is implemented inside the BiCGSTAB main solver");
 }
 
 static void destroy(pps_handle* h);
@@ -2459,6 +2582,8 @@ int pps_apply_preconditioner(pps_handle* h, int rank, const double* b_host, doub
     PPS_API_BEGIN
     if (h->operator_only) throw std::runtime_error("pps_apply_preconditioner: handle is operator-only (PPS_FLAG_OPERATOR_ONLY)");
     PPS_CUDA_CHECK(cudaSetDevice(h->device));
+    if (h->precond_comm && h->cfg.precond == PPS_PRECOND_BICGSTAB_LOCAL)
+        throw std::runtime_error("pps_apply_preconditioner applies a block-local preconditioner; the global nested BiCGSTAB is collective");
     Block* b = find_block(h, rank);
     upload_field(h, *b, b->p, b_host);
     if (b->mp != b->p) zero_field(h, *b, b->mp);

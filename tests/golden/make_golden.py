@@ -47,6 +47,9 @@ CASES = [
     # nested Krylov preconditioners
     ("nb24", (1, 1, 1), True), ("nb24", (1, 1, 2), False), ("nb24", (3, 1, 2), False),
     ("nc24", (1, 1, 1), True), ("nc24", (2, 2, 1), False), ("nc24", (3, 1, 2), False),
+    # GLOBAL nested BiCGSTAB preconditioner (communicationON in the preconditioner slot; alpaka: T_PreconditionerBiCGStabGlobal)
+    ("nbg24", (1, 1, 2), True), ("nbg24_i8", (1, 1, 1), True), ("nbg24_i8", (1, 1, 2), True), ("nbg24_i8", (2, 2, 1), False), ("nbg24_i8", (3, 1, 2), False),
+    ("nbgd32", (2, 2, 2), False),
     # first-order Neumann closure (orderNeumanBcs = 1): BiCGSTAB, BiCGSTAB + Chebyshev, CG (which then resets ghosts)
     ("o1m24", (1, 1, 1), True), ("o1m24", (1, 1, 2), False), ("o1m24", (3, 1, 2), False),
     ("o1m24_cheb", (1, 1, 1), True), ("o1m24_cheb", (2, 2, 1), False),
@@ -131,6 +134,7 @@ def run_case(name, ranks, store_x):
             order_neumann=c.get("order_neumann", 2), dim=c.get("dim", 3),
             cheb_rescale_min=500.0 if c.get("rescale_min") is None else float(c["rescale_min"]),
             cheb_rescale_max=1 - 1e-4 if c.get("rescale_max") is None else float(c["rescale_max"]),
+            precond_max_iter=150 if c.get("precond_iter_max") is None else int(c["precond_iter_max"]),
         )
         if store_x is True:
             out["x"] = assemble(td, world, c["np"])

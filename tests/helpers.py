@@ -30,9 +30,11 @@ def oracle_config_from_golden(g, nranks=None, max_iter=None, tolerance=None):
     if "dim" in g:
         extra["dim"] = int(g["dim"])
     precond = {"cheb": po.PRECOND_CHEBYSHEV, "chebglobal": po.PRECOND_CHEBYSHEV, "bicgloc": po.PRECOND_BICGSTAB_LOCAL,
-               "cgcheb": po.PRECOND_CG_CHEB_LOCAL}.get(str(g["precond"]), po.PRECOND_NONE)
-    if str(g["precond"]) == "chebglobal":
+               "bicgglob": po.PRECOND_BICGSTAB_LOCAL, "cgcheb": po.PRECOND_CG_CHEB_LOCAL}.get(str(g["precond"]), po.PRECOND_NONE)
+    if str(g["precond"]) in ("chebglobal", "bicgglob"):
         extra["precond_comm"] = 1
+    if "precond_max_iter" in g:
+        extra["precond_max_iter"] = int(g["precond_max_iter"])
     return po.make_config(
         np_=[int(v) for v in g["np"]], nranks=[int(v) for v in (g["nranks"] if nranks is None else nranks)],
         ds=[float(v) for v in g["ds"]], origin=[float(v) for v in g["origin"]], bcs=[int(v) for v in g["bcs"]],

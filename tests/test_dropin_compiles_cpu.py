@@ -17,6 +17,7 @@ pytestmark = pytest.mark.skipif(not br.available() or not os.path.exists(LIB),
 # config -> what it exercises in the adapters
 STACKS = {
     "nb24": "BiCGSTAB + nested local BiCGSTAB (T_Preconditioner, inputParam.hpp:31)",
+    "nbg24_i8": "BiCGSTAB + nested GLOBAL BiCGSTAB (BiCGSTAB<.., false, communicationON, NoneSolver>; alpaka T_PreconditionerBiCGStabGlobal)",
     "nc24": "BiCGSTAB + nested local CG with Chebyshev inside (T_Preconditioner3, inputParam.hpp:29)",
     "chm24": "ChebyshevIteration as T_Solver (isMainLoop, communicationON)",
     "o1cgm24": "BaseCG, orderNeumanBcs = 1",

@@ -134,6 +134,46 @@ def test_nested_preconditioner_against_reference_golden(name):
     s.close(); o.close()
 
 
+@pytest.mark.parametrize("name", ["nbg24_112", "nbg24_i8_111", "nbg24_i8_112", "nbg24_i8_221", "nbg24_i8_312", "nbgd32_222"])
+def test_global_nested_bicgstab_against_reference_golden(name):
+    """BiCGSTAB<.., isMainLoop = false, communicationON, NoneSolver> in the preconditioner slot (the alpaka tree's
+    T_PreconditionerBiCGStabGlobal): the nested solve spans all blocks -- face exchanges and global reductions inside the
+    preconditioner (nested_bicgstab_global).  Fixtures from the unmodified reference; `_i8`: iterMaxPreconditioner = 8, so the
+    nested solves stop on the iteration cap and the outer solve takes 22-29 iterations; the others converge the nested solve to
+    1e-6 and need ONE outer iteration.  Same bar as the local nested solvers."""
+    g, o, s = _from_golden(name)
+    s.solve()
+    it = int(g["iters"])
+    hs, hg = s.history(), g["history"]
+    n = min(4, len(hs), len(hg))
+    H.record_margin("global_nested_bicgstab", golden=name, iters=s.iterations, iters_reference=it,
+                    hist_rel_first4=float(np.max(np.abs(hs[:n] - hg[:n]) / hg[:n])), true_residual=s.error_operator,
+                    nested_iterations=s.preconditioner_iterations)
+    assert abs(s.iterations - it) <= max(2, it // 4), (s.iterations, it)
+    assert abs(s.norm_b - float(g["norm_b"])) <= 1e-13 * float(g["norm_b"])
+    if it > 3:
+        assert np.max(np.abs(hs[:n] - hg[:n]) / hg[:n]) <= 1e-2
+    assert s.error_operator < 1.5 * float(g["tolerance"])
+    assert s.preconditioner_iterations > 0
+    if "x" in g:
+        assert H.rel_l2(H.pps_global_solution(s, o.cfg), g["x"]) <= 2e-6
+    s.close(); o.close()
+
+
+def test_global_nested_bicgstab_is_layout_independent():
+    """a GLOBAL nested solve is the same algorithm on every block layout: with the iteration cap active the outer iteration counts
+    of 1, 2 and 6 blocks stay within the reference's own spread (26 / 22 / 25 there), unlike the block-local variant whose
+    preconditioner weakens with the number of blocks"""
+    its = []
+    for name in ("nbg24_i8_111", "nbg24_i8_112", "nbg24_i8_312"):
+        g, o, s = _from_golden(name)
+        s.solve()
+        assert s.error_operator < 1.5 * float(g["tolerance"])
+        its.append(s.iterations)
+        s.close(); o.close()
+    assert max(its) - min(its) <= 8, its
+
+
 # ---------------------------------------------------------------- DIM = 2 and DIM = 1
 LOWDIM = [(2, (24, 20, 1), (0, 1, 0, 1, 0, 0)), (2, (67, 9, 1), (1, 0, 1, 0, 0, 0)), (2, (130, 7, 1), (0, 0, 0, 0, 0, 0)),
           (1, (48, 1, 1), (0, 1, 0, 0, 0, 0)), (1, (131, 1, 1), (1, 0, 0, 0, 0, 0))]
