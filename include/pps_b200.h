@@ -90,8 +90,11 @@ typedef struct pps_config {
     int cheb_precision;       /* PPS_CHEB_FP*: T_data_chebyshev of solverPoissonMPI_alpaka/include/solverSetup.hpp:14 */
     int cheb_block;           /* Chebyshev sweeps advanced per HBM pass by the temporally blocked kernel (0 = one kernel per sweep, 1..4) */
     int precond_communication; /* communicationON / OFF template argument of the preconditioner (inputParam.hpp:20-21,28): 0 = OFF, block-Jacobi
-                                  (shipped); 1 = ON, the Chebyshev preconditioner exchanges the faces of B and of every iterate
-                                  (chebyshevIteration.hpp:69-73,97-101) -- a global polynomial preconditioner */
+                                  (shipped); 1 = ON: the Chebyshev preconditioner exchanges the faces of B and of every iterate
+                                  (chebyshevIteration.hpp:69-73,97-101) -- a global polynomial preconditioner; with
+                                  PPS_PRECOND_BICGSTAB_LOCAL the nested BiCGSTAB becomes ONE solve over all blocks / GPUs (face exchanges
+                                  and allreduces inside the preconditioner, BiCGSTAB.hpp:135-139,156-164,182-186,216-225,247-257 with
+                                  isMainLoop = false; solverPoissonMPI_alpaka/include/inputParam.hpp:33 T_PreconditionerBiCGStabGlobal) */
 } pps_config;
 
 /* pps_config.flags */

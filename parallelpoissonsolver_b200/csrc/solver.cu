@@ -1915,6 +1915,8 @@ static void validate(const pps_config& c, int rank, int world) {
         (c.precond != PPS_PRECOND_CHEBYSHEV || c.cheb_precision != PPS_CHEB_FP64 || c.cheb_eigenvalues != PPS_CHEB_EIG_GLOBAL))
         throw std::runtime_error("precond_communication = 1 is implemented for the fp64 Chebyshev preconditioner with global eigenvalue bounds "
                                  "and for the nested BiCGSTAB (BiCGSTAB<.., false, communicationON, NoneSolver>)");
+    if (c.cheb_precision == PPS_CHEB_FP32 && c.dim != 3 && (c.precond == PPS_PRECOND_CHEBYSHEV || c.precond == PPS_PRECOND_CG_CHEB_LOCAL))
+        throw std::runtime_error("cheb_precision = PPS_CHEB_FP32 (T_data_chebyshev = float) is implemented for DIM = 3 only");
     if (c.precond_communication == 1 && c.precond == PPS_PRECOND_BICGSTAB_LOCAL && c.solver != PPS_SOLVER_BICGSTAB)
         throw std::runtime_error("the global nested BiCGSTAB preconditioner is implemented inside the BiCGSTAB main solver");
 }
