@@ -1,7 +1,8 @@
 """GPU parity tests of the SURVEY.md section 8(f) items: first-order Neumann closure (orderNeumanBcs = 1), Chebyshev iteration
 as MAIN solver, nested Krylov preconditioners (local BiCGSTAB, local CG + Chebyshev), DIM = 2 and DIM = 1.  The oracle side of
-each is pinned bit for bit to the unmodified reference on the CPU (tests/test_oracle.py).  Verified on B200 in round 2
-(profiles/r02_validation_summary.txt), part of the default GPU suite since."""
+each is pinned bit for bit to the unmodified reference on the CPU (tests/test_oracle.py).  Verified on B200 in round 2, part of the
+default GPU suite since; the GLOBAL nested BiCGSTAB preconditioner (communicationON in the preconditioner slot) joined at the end of
+round 2 (margins: profiles/r02_parity_margins_alpaka.jsonl)."""
 import numpy as np
 import pytest
 
@@ -152,7 +153,9 @@ def test_global_nested_bicgstab_against_reference_golden(name):
     assert abs(s.iterations - it) <= max(2, it // 4), (s.iterations, it)
     assert abs(s.norm_b - float(g["norm_b"])) <= 1e-13 * float(g["norm_b"])
     if it > 3:
-        assert np.max(np.abs(hs[:n] - hg[:n]) / hg[:n]) <= 1e-2
+        # the nested solves run to the iteration cap: a fixed algorithm, so the outer history is in lock-step to rounding
+        # (measured on B200: 7e-12 .. 1.7e-10 over the first four entries; iterations 23/26, 21/22, 24/29, 25/25)
+        assert np.max(np.abs(hs[:n] - hg[:n]) / hg[:n]) <= 1e-6
     assert s.error_operator < 1.5 * float(g["tolerance"])
     assert s.preconditioner_iterations > 0
     if "x" in g:
