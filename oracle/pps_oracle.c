@@ -456,8 +456,8 @@ static void chebyshev_block(orc_t* o, int rank, double* X, double* Bf) {
 /* Mixed-precision Chebyshev preconditioner of the alpaka tree (T_data_chebyshev = float), communicationOFF:
  * chebyshevIterationAlpaka.hpp:116-310 (host loop, `cast` branch :149-190, X = -W :293-294) with the kernels
  * CastPrecisionFieldKernel (kernelsAlpakaChebyshev.hpp:8-18), Chebyshev1Kernel (:136-183), Chebyshev2Kernel (:233-270) and
- * AssignFieldWith1FieldKernel (:24-45).  RESTATEMENT ONLY: the alpaka tree cannot be built in this image (alpaka, Boost, MPI),
- * so nothing pins these lines to a run of the reference -- parity unpinned.  Every operation is a float operation in the
+ * AssignFieldWith1FieldKernel (:24-45).  PINNED bit for bit against the unmodified alpaka tree built with its OpenMP CPU accelerator
+ * (oracle/build_ref_alpaka.py; tests/golden/alpaka/alp_f32*.npz, tests/test_oracle_alpaka.py).  Every operation is a float operation in the
  * kernels' own order, no contraction (this file is compiled with -ffp-contract=off).
  * The alpaka tree's delta has the opposite sign of the CPU tree's (chebyshevIterationAlpaka.hpp:29), hence -B->delta. */
 static void chebyshev_block_alpaka_f32(orc_t* o, int rank, double* X, double* Bf) {

@@ -8,7 +8,8 @@
  * rank order 0..n-1 -- the same arithmetic, operation for operation, as the
  * reference built against oracle/mpi_shim (whose Allreduce also sums in rank
  * order), so residual histories and solutions agree BIT FOR BIT with oracle/_ref
- * (pinned by tests/test_oracle_vs_ref.py and the fixtures in tests/golden/).
+ * (pinned by tests/test_oracle.py on the fixtures in tests/golden/, which tests/golden/make_golden.py
+ * generates from the unmodified reference).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use
  * this.  The product (libpps_b200.so) never links or calls it.
@@ -24,7 +25,8 @@ enum { ORC_SOLVER_BICGSTAB = 0, ORC_SOLVER_CG = 1,
        ORC_SOLVER_CHEBYSHEV = 2 /* ChebyshevIteration<..., isMainLoop = true, communicationON, NoneSolver>: chebyshevIteration.hpp:48-140; cheb_max sweeps, no normalisation, no history */ };
 enum { ORC_PRECOND_NONE = 0,            /* T_NoneSolver,       inputParam.hpp:24 */
        ORC_PRECOND_CHEBYSHEV = 1,       /* T_Preconditioner2,  inputParam.hpp:28 */
-       ORC_PRECOND_BICGSTAB_LOCAL = 2,  /* T_Preconditioner,   inputParam.hpp:31: BiCGSTAB, isMainLoop false, communicationOFF, NoneSolver inside */
+       ORC_PRECOND_BICGSTAB_LOCAL = 2,  /* T_Preconditioner,   inputParam.hpp:31: BiCGSTAB, isMainLoop false, communicationOFF, NoneSolver inside
+                                           (with orc_config.precond_comm = 1: communicationON, a global nested solve) */
        ORC_PRECOND_CG_CHEB_LOCAL = 3    /* T_Preconditioner3,  inputParam.hpp:29: BaseCG, isMainLoop false, communicationOFF, Chebyshev inside */ };
 
 typedef struct orc_config {
@@ -45,12 +47,15 @@ typedef struct orc_config {
     int precond_max_iter;     /* iterMaxPreconditioner   solverSetup.hpp:32 */
     int order_neumann;        /* orderNeumanBcs: 2 (shipped) or 1   solverSetup.hpp:25 */
     int dim;                  /* DIM: 3 (shipped), 2 or 1   inputParam.hpp:16; axes >= dim hold one point, no guards (blockGrid.hpp:160-206) */
-    /* alpaka-only configuration surface (solverPoissonMPI_alpaka; that tree needs alpaka + Boost + MPI and cannot be built here, so
-     * these two are a RESTATEMENT ONLY -- parity unpinned, see the functions that use them) */
+    /* alpaka-only configuration surface (solverPoissonMPI_alpaka).  PINNED: oracle/build_ref_alpaka.py builds that tree unmodified with
+     * alpaka's OpenMP CPU accelerator (vendored alpaka 1.2.0 + mdspan, oracle/boost_shim, oracle/mpi_shim); the fp32 preconditioner agrees
+     * bit for bit with it, the fp64 one to 2e-15 (tests/golden/alpaka/, tests/test_oracle_alpaka.py) */
     int cheb_eig_local;       /* 1: `local` of solverPoissonMPI_alpaka/include/inputParam.hpp:21-22: block-local, not rescaled eigenvalue bounds */
     int cheb_f32;             /* 1: T_data_chebyshev = float, solverPoissonMPI_alpaka/include/solverSetup.hpp:14 (mixed-precision preconditioner) */
-    int precond_comm;         /* 1: the Chebyshev preconditioner runs with communicationON (face exchange of B and of every iterate,
-                                 chebyshevIteration.hpp:69-73,97-101) -- a GLOBAL polynomial preconditioner instead of block-Jacobi */
+    int precond_comm;         /* 1: the preconditioner runs with communicationON.  ORC_PRECOND_CHEBYSHEV: face exchange of B and of every iterate
+                                 (chebyshevIteration.hpp:69-73,97-101) -- a GLOBAL polynomial preconditioner instead of block-Jacobi.
+                                 ORC_PRECOND_BICGSTAB_LOCAL: the nested BiCGSTAB is ONE solve over all ranks (exchanges and allreduces inside the
+                                 preconditioner; BiCGSTAB.hpp:55-322 with isMainLoop = false, communicationON = true) */
 } orc_config;
 
 typedef struct orc_block_info {

@@ -184,8 +184,8 @@ def test_oracle_matches_reference_binary_live(ranks):
 
 # ---------------------------------------------------------------- alpaka-only configuration surface
 def test_oracle_fp32_chebyshev_tracks_the_fp64_preconditioner():
-    """The restatement of the alpaka tree's mixed-precision Chebyshev (kernelsAlpakaChebyshev.hpp, T_data_chebyshev = float; parity
-    unpinned: that tree cannot be built here) must be the SAME polynomial as the CPU tree's fp64 preconditioner up to float
+    """The restatement of the alpaka tree's mixed-precision Chebyshev (kernelsAlpakaChebyshev.hpp, T_data_chebyshev = float; pinned to
+    the unmodified alpaka tree in tests/test_oracle_alpaka.py) must be the SAME polynomial as the CPU tree's fp64 preconditioner up to float
     rounding: same theta, the alpaka sign of delta, the same X = -y_{n-2} quirk."""
     res = {}
     for f32 in (0, 1):
