@@ -40,9 +40,12 @@ SOLVER_TYPEDEFS = {
     "bicgstab_none": _MAIN % "T_NoneSolverAlpaka",
     "bicgstab_chebglobal": _MAIN % "T_PreconditionerChebGlobal",   # the tree as shipped, inputParam.hpp:36
     "bicgstab_cheblocal": _MAIN % "T_PreconditionerChebLocal",     # `local`, inputParam.hpp:27
+    "bicgstab_bicgloc": _MAIN % "T_PreconditionerBiCGStabLocal",   # nested block-local BiCGSTAB, inputParam.hpp:31
+    "bicgstab_bicgglob": _MAIN % "T_PreconditionerBiCGStabGlobal",  # nested GLOBAL BiCGSTAB (communicationON), inputParam.hpp:33
 }
 PRECOND_TYPEDEF = {"bicgstab_none": "T_NoneSolverAlpaka", "bicgstab_chebglobal": "T_PreconditionerChebGlobal",
-                   "bicgstab_cheblocal": "T_PreconditionerChebLocal"}
+                   "bicgstab_cheblocal": "T_PreconditionerChebLocal", "bicgstab_bicgloc": "T_PreconditionerBiCGStabLocal",
+                   "bicgstab_bicgglob": "T_PreconditionerBiCGStabGlobal"}
 
 DIRICHLET = (0, 0, 0, 0, 0, 0)
 MIXED = (0, 1, 0, 1, 0, 1)
@@ -50,11 +53,13 @@ M24 = dict(np=(24, 20, 28), bcs=MIXED, ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 
 
 
 def cfg(np, bcs=DIRICHLET, solver="bicgstab_chebglobal", cheb_type="double", ds=(0.1, 0.1, 0.1), origin=(0, 0, 0),
-        toll_scaling=1e-8, toll_main=1, iter_max=1700, cheb_max=11, rescale_min=500.0, rescale_max=1 - 1e-4, write_files=False):
-    # (toll_main stays 1: tollPreconditionerSolver = tollMainSolver * 1e8 must fit an int, solverSetup.hpp:63)
+        toll_scaling=1e-8, toll_main=1, iter_max=1700, cheb_max=11, rescale_min=500.0, rescale_max=1 - 1e-4, write_files=False,
+        toll_precond=None, precond_iter_max=None):
+    # (toll_main stays 1 unless toll_precond is given: tollPreconditionerSolver = tollMainSolver * 1e8 must fit an int, solverSetup.hpp:63)
     return dict(np=tuple(np), bcs=tuple(bcs), solver=solver, cheb_type=cheb_type, ds=tuple(ds), origin=tuple(origin),
                 toll_scaling=toll_scaling, toll_main=toll_main, iter_max=iter_max, cheb_max=cheb_max,
-                rescale_min=rescale_min, rescale_max=rescale_max, write_files=write_files)
+                rescale_min=rescale_min, rescale_max=rescale_max, write_files=write_files, toll_precond=toll_precond,
+                precond_iter_max=precond_iter_max)
 
 
 CONFIGS = {
@@ -71,6 +76,11 @@ CONFIGS = {
     # fp64 global: the alpaka kernels' folded 7-point form against the CPU tree's expression order
     "alp_f64_m24": cfg(**M24),
     "alp_none_m24": cfg(solver="bicgstab_none", **M24),
+    # nested Krylov preconditioners of the alpaka tree (inputParam.hpp:31,33) with the CPU tree's settings: main tolerance 100 * 1e-10,
+    # nested tolerance 1e4 * 1e-10, nested iteration cap 150 (or 8: the nested solves then stop on the cap)
+    "alp_nbl_m24": cfg(solver="bicgstab_bicgloc", toll_scaling=1e-10, toll_main=100, toll_precond=10000, precond_iter_max=150, **M24),
+    "alp_nbg_m24": cfg(solver="bicgstab_bicgglob", toll_scaling=1e-10, toll_main=100, toll_precond=10000, precond_iter_max=150, **M24),
+    "alp_nbg_m24_i8": cfg(solver="bicgstab_bicgglob", toll_scaling=1e-10, toll_main=100, toll_precond=10000, precond_iter_max=8, **M24),
     # writeResidual / writeSolution = true (inputParam.hpp:46-47): residualHistory.txt and solution.dat from the tree's own main.cpp
     "alp_files_m24": cfg(write_files=True, **M24),
 }
@@ -105,6 +115,10 @@ def make_cfg_dir(name, c):
     t = _sub(t, r"chebyshevMax=[^;]*;", "chebyshevMax=%d;" % c["cheb_max"], p)
     t = _sub(t, r"rescaleEigMin= [^;]*;", "rescaleEigMin= %s;" % _fmt(float(c["rescale_min"])), p)
     t = _sub(t, r"rescaleEigMax= [^;]*;", "rescaleEigMax= %s;" % _fmt(float(c["rescale_max"])), p)
+    if c.get("toll_precond") is not None:
+        t = _sub(t, r"tollPreconditionerSolver=[^;]*;", "tollPreconditionerSolver=%d;" % c["toll_precond"], p)
+    if c.get("precond_iter_max") is not None:
+        t = _sub(t, r"iterMaxPreconditioner=[^;]*;", "iterMaxPreconditioner=%d;" % c["precond_iter_max"], p)
     open(p, "w").write(t)
     return dst
 

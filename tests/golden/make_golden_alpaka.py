@@ -4,8 +4,9 @@ alpaka's OpenMP-blocks CPU accelerator by oracle/build_ref_alpaka.py; run with O
 reductions are ordered).  These fixtures pin the alpaka-only configuration surface: fp32 Chebyshev
 iterates (solverSetup.hpp:14) and block-local eigenvalue bounds (inputParam.hpp:21-22,27).  Per (config, px py pz) case:
 
-    precond_x     ChebyshevIterationAlpaka::operator()(bufX, bufB) (chebyshevIterationAlpaka.hpp:119-310) applied ONCE to the test
-                  field of oracle/ref_dump_alpaka.cpp (`alpaka_test_field` below builds the same numbers); X on the global data range
+    precond_x     the preconditioner class -- ChebyshevIterationAlpaka::operator()(bufX, bufB) (chebyshevIterationAlpaka.hpp:119-310) or
+                  the nested BiCGstabAlpaka::operator()(bufX, bufB) (BiCGstabAlpaka.hpp:480-861) -- applied ONCE to the test field of
+                  oracle/ref_dump_alpaka.cpp (`alpaka_test_field` below builds the same numbers); X on the global data range
     history, iters, precond_iters, error_iteration, error_operator, max_point_error       one full solve (src/main.cpp:83-101)
     np, nranks, ds, origin, bcs, tolerance, max_iter, cheb_max, cheb_rescale_min/max, cheb_f32, cheb_eig_local, precond  (the configuration)
 Only runnable where /root/reference exists (the build container); the fixtures travel.
@@ -36,7 +37,13 @@ CASES = [
     ("alp_loc_m24", (1, 1, 2)), ("alp_loc_m24", (2, 2, 1)),
     ("alp_f64_m24", (1, 1, 1)), ("alp_none_m24", (1, 1, 1)),
     ("alp_shipped32", (1, 1, 1)), ("alp_shipped32", (1, 1, 2)),
+    # nested BiCGSTAB preconditioners of the alpaka tree (inputParam.hpp:31,33).  (The block-local one on more than one rank does not
+    # finish within minutes in the alpaka tree itself -- not used.)
+    ("alp_nbl_m24", (1, 1, 1)),
+    ("alp_nbg_m24", (1, 1, 1)), ("alp_nbg_m24", (1, 1, 2)), ("alp_nbg_m24", (2, 2, 1)),
+    ("alp_nbg_m24_i8", (1, 1, 1)), ("alp_nbg_m24_i8", (1, 1, 2)), ("alp_nbg_m24_i8", (3, 1, 2)),
 ]
+TIMEOUT = 600
 
 
 def alpaka_test_field(gk, gj, gi):
@@ -82,15 +89,17 @@ def run_case(name, ranks):
                bcs=np.array(c["bcs"]), tolerance=float(c["toll_main"] * c["toll_scaling"]), max_iter=int(c["iter_max"]),
                cheb_max=int(c["cheb_max"]), cheb_rescale_min=float(c["rescale_min"]), cheb_rescale_max=float(c["rescale_max"]),
                cheb_f32=int(c["cheb_type"] == "float"), cheb_eig_local=int(c["solver"] == "bicgstab_cheblocal"),
-               precond="none" if c["solver"] == "bicgstab_none" else "cheb")
-    if out["precond"] == "cheb":
+               precond={"bicgstab_none": "none", "bicgstab_bicgloc": "bicgloc", "bicgstab_bicgglob": "bicgglob"}.get(c["solver"], "cheb"),
+               precond_tolerance=float((c.get("toll_precond") or c["toll_main"] * 1e8) * c["toll_scaling"]),
+               precond_max_iter=int(c.get("precond_iter_max") or 500))
+    if out["precond"] != "none":
         with tempfile.TemporaryDirectory() as td:
-            subprocess.run([exe, *map(str, ranks), td, "precond"], check=True, capture_output=True, text=True, env=env)
+            subprocess.run([exe, *map(str, ranks), td, "precond"], check=True, capture_output=True, text=True, env=env, timeout=TIMEOUT)
             for r in range(world):   # assemble() reads rank<r>.x
                 os.rename(f"{td}/rank{r}.px", f"{td}/rank{r}.x")
             out["precond_x"] = assemble(td, world, c["np"])
     with tempfile.TemporaryDirectory() as td:
-        r = subprocess.run([exe, *map(str, ranks), td, "solve"], check=True, capture_output=True, text=True, env=env)
+        r = subprocess.run([exe, *map(str, ranks), td, "solve"], check=True, capture_output=True, text=True, env=env, timeout=TIMEOUT)
         s = read_summary(td + "/summary.txt")
         maxerr = [l for l in r.stdout.splitlines() if l.startswith("Max error local point")]
         out.update(history=np.fromfile(td + "/history.bin"), iters=int(s["iters"][0]), precond_iters=int(s["precond_iters"][0]),

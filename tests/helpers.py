@@ -46,8 +46,10 @@ def oracle_config_from_golden(g, nranks=None, max_iter=None, tolerance=None):
 ALPAKA_GOLDEN = os.path.join(GOLDEN, "alpaka")
 
 
-def alpaka_golden_names(precond_only=False):
+def alpaka_golden_names(precond_only=False, nested=False):
+    """fixtures of the Chebyshev switches (default) or of the nested BiCGSTAB preconditioners (`nested`)"""
     names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(ALPAKA_GOLDEN, "alp_*.npz")))
+    names = [n for n in names if n.startswith("alp_nb") == bool(nested)]
     return [n for n in names if not (precond_only and n.startswith("alp_none"))]
 
 
@@ -59,12 +61,17 @@ def load_alpaka_golden(name):
 def oracle_config_from_alpaka_golden(g):
     """the alpaka tree's configuration surface (solverPoissonMPI_alpaka/include/inputParam.hpp, solverSetup.hpp): epsilon = 0,
     T_data_chebyshev and the local / global eigenvalue switch"""
+    kind = str(g["precond"])
+    extra = {}
+    if kind in ("bicgloc", "bicgglob"):   # nested BiCGSTAB, block-local / global (inputParam.hpp:31,33)
+        extra = dict(precond_tolerance=float(g["precond_tolerance"]), precond_max_iter=int(g["precond_max_iter"]), precond_comm=int(kind == "bicgglob"))
     return po.make_config(
         np_=[int(v) for v in g["np"]], nranks=[int(v) for v in g["nranks"]], ds=[float(v) for v in g["ds"]],
         origin=[float(v) for v in g["origin"]], bcs=[int(v) for v in g["bcs"]],
-        precond=po.PRECOND_CHEBYSHEV if str(g["precond"]) == "cheb" else po.PRECOND_NONE, tolerance=float(g["tolerance"]),
+        precond={"cheb": po.PRECOND_CHEBYSHEV, "bicgloc": po.PRECOND_BICGSTAB_LOCAL, "bicgglob": po.PRECOND_BICGSTAB_LOCAL}.get(kind, po.PRECOND_NONE),
+        tolerance=float(g["tolerance"]),
         max_iter=int(g["max_iter"]), cheb_max=int(g["cheb_max"]), cheb_epsilon=0.0, cheb_rescale_min=float(g["cheb_rescale_min"]),
-        cheb_rescale_max=float(g["cheb_rescale_max"]), cheb_f32=int(g["cheb_f32"]), cheb_eig_local=int(g["cheb_eig_local"]))
+        cheb_rescale_max=float(g["cheb_rescale_max"]), cheb_f32=int(g["cheb_f32"]), cheb_eig_local=int(g["cheb_eig_local"]), **extra)
 
 
 def alpaka_test_field(gk, gj, gi):
