@@ -1,7 +1,10 @@
 #!/usr/bin/env python3
 """Multi-GPU parity check, one process per GPU (run under torchrun; tests/test_gpu_multi.py drives it).
 
-    torchrun --nproc-per-node N tools/mg_check.py PX PY PZ [cheb] [cg]
+    torchrun --nproc-per-node N tools/mg_check.py PX PY PZ [cheb | chebg | nbg] [cg] [fusecmp]
+        cheb   block-Jacobi Chebyshev(11) preconditioner        chebg  the same with communicationON (global polynomial)
+        nbg    GLOBAL nested BiCGSTAB preconditioner, nested solves capped at 8 iterations (validated on one GPU hosting all
+               blocks at the end of round 2; this flag is how its one-block-per-GPU NCCL leg gets its first multi-GPU run)
 
 Every rank hosts its block of the PX x PY x PZ decomposition on its own GPU (NCCL halo exchange + allreduce);
 the CPU oracle runs the same layout in one process; rank 0 compares ||b||, the residual history and, after a
@@ -44,7 +47,9 @@ def main():
     np_ = (24 * px if px > 1 else 40, 20 * py if py > 1 else 24, 16 * pz if pz > 1 else 20)
     ocfg = po.make_config(np_, (px, py, pz), ds=(0.1, 0.12, 0.09), origin=(0.3, -0.2, 0.1), bcs=(0, 1, 0, 1, 0, 1),
                           solver=po.SOLVER_CG if "cg" in flags else po.SOLVER_BICGSTAB,
-                          precond=po.PRECOND_CHEBYSHEV if "cheb" in flags else po.PRECOND_NONE, tolerance=1e-8)
+                          precond=(po.PRECOND_BICGSTAB_LOCAL if "nbg" in flags else
+                                   po.PRECOND_CHEBYSHEV if ("cheb" in flags or "chebg" in flags) else po.PRECOND_NONE),
+                          precond_comm=int("nbg" in flags or "chebg" in flags), precond_max_iter=8 if "nbg" in flags else 150, tolerance=1e-8)
     if "cg" in flags:
         ocfg.bcs[:] = [0] * 6
     o = po.Oracle(ocfg)
@@ -99,6 +104,13 @@ def main():
         ok = (out["norm_b_rel"] <= 1e-13 and d10 <= 1e-11 and d20 <= 1e-7 and rel <= 2e-6 and
               0.85 * o.iters - 2 <= s.iterations <= 1.15 * o.iters + 2 and s.error_operator < 1.5e-8 and
               fused_equals_split is not False)
+        if "nbg" in flags:
+            # capped nested solves: lock-step over the first entries, iteration counts scatter (tests/test_gpu_next.py)
+            n4 = min(4, len(ho), len(hs))
+            out["hist4"] = float(np.max(np.abs(hs[:n4] - ho[:n4]) / ho[:n4]))
+            out["nested_iterations"] = s.preconditioner_iterations
+            ok = (out["norm_b_rel"] <= 1e-13 and out["hist4"] <= 1e-6 and rel <= 2e-6 and s.error_operator < 1.5e-8 and
+                  abs(s.iterations - o.iters) <= max(2, o.iters // 4))
         try:
             H.record_margin("multi_gpu_vs_oracle", **{k: v for k, v in out.items() if k != "flags"}, flags=list(flags))
         except Exception:
