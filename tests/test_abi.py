@@ -63,3 +63,27 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setenv("PPS_B200_LIBRARY", "/nonexistent/libpps_b200.so")
     with pytest.raises(pps.PpsError):
         api.load_library()
+
+
+def test_config_validation_runs_before_any_device_work():
+    """pps_create validates the configuration first (csrc/solver.cu validate()), so refusals are testable without a GPU: stacks the
+    library does not implement are refused with a message instead of running something else; the accepted global nested BiCGSTAB
+    gets as far as the device (and fails there on a CPU-only box: there is no CPU fallback)."""
+    import parallelpoissonsolver_b200 as pps
+    refused = [
+        (dict(npglobal=(24, 20, 1), dim=2, precond=pps.PRECOND_CHEBYSHEV, cheb_precision=pps.CHEB_FP32), "DIM = 3 only"),
+        (dict(npglobal=(24, 20, 28), precond=pps.PRECOND_CG_CHEB_LOCAL, precond_communication=1), "precond_communication = 1 is implemented for"),
+        (dict(npglobal=(24, 20, 28), precond=pps.PRECOND_BICGSTAB_LOCAL, precond_communication=1, solver=pps.SOLVER_CG), "inside the BiCGSTAB main solver"),
+        (dict(npglobal=(24, 20, 28), precond=pps.PRECOND_CHEBYSHEV, precond_communication=1, cheb_precision=pps.CHEB_FP32), "precond_communication = 1 is implemented for"),
+        (dict(npglobal=(24, 20, 28), solver=pps.SOLVER_CHEBYSHEV, precond=pps.PRECOND_CHEBYSHEV), "takes no preconditioner"),
+        (dict(npglobal=(24, 20, 28), nranks=(1, 1, 16)), "at least 3 points"),
+    ]
+    for kw, needle in refused:
+        with pytest.raises(pps.PpsError) as e:
+            pps.PoissonSolver(pps.make_config(**kw))
+        assert needle in str(e.value), (kw, str(e.value))
+    try:
+        s = pps.PoissonSolver(pps.make_config(npglobal=(24, 20, 28), nranks=(1, 1, 2), precond=pps.PRECOND_BICGSTAB_LOCAL, precond_communication=1))
+        s.close()
+    except pps.PpsError as e:
+        assert "CUDA" in str(e), str(e)
