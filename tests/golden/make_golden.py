@@ -66,6 +66,9 @@ CASES = [
     ("l48_cheb", (1, 1, 1), True), ("l48_cheb", (2, 1, 1), False),
     # GLOBAL Chebyshev preconditioner (communicationON in the preconditioner slot)
     ("d32_chebg", (1, 1, 2), True), ("d32_chebg", (2, 2, 2), False), ("m24_chebg", (1, 1, 2), True), ("m24_chebg", (3, 2, 1), False),
+    # edge cases: non-divisible grid (truncated blocks), smallest blocks
+    ("e25", (2, 2, 2), True), ("e25", (1, 1, 2), True), ("e25_cheb", (2, 2, 2), True), ("e25_cheb", (1, 2, 1), False),
+    ("tiny6", (1, 1, 1), True), ("tiny6", (2, 2, 2), True), ("tiny6_cheb", (2, 2, 2), True), ("tiny6_cheb", (1, 1, 2), True),
     # the benchmarked configurations and their neighbours: full solves at 128^3 and 256^3, the first 20
     # iterations at 512^3.  An integer instead of True stores x on the sub-lattice of every s-th global point ("x_sample").
     # (bench1024_it20 needs ~110 GB of host memory: tools/make_golden_1024.py runs it on the GPU box's host)

@@ -29,6 +29,8 @@ CASES = [
     (3, (128, 128, 256), (4, 4, 4), (0, 1, 0, 1, 0, 1)),
     (3, (24, 20, 28), (3, 2, 1), (1, 0, 0, 1, 1, 1)),
     (3, (67, 9, 12), (1, 1, 4), (0, 0, 0, 0, 0, 0)),
+    (3, (25, 21, 29), (2, 2, 2), (0, 1, 0, 1, 0, 1)),    # the rank grid does not divide the grid: nlocal = npglobal / nranks truncates (blockGrid.hpp:165)
+    (3, (6, 6, 6), (2, 2, 2), (0, 0, 0, 0, 0, 0)),       # smallest blocks: 3 points per axis
     (2, (24, 20, 1), (3, 2, 1), (0, 1, 0, 1, 0, 1)),
     (2, (40, 36, 1), (2, 3, 1), (0, 0, 0, 0, 0, 0)),
     (2, (40, 36, 7), (1, 1, 1), (1, 1, 1, 0, 0, 0)),     # npglobal[2] is ignored for DIM = 2 (blockGrid.hpp:166-167)

@@ -13,7 +13,7 @@ from oracle import pyoracle as po
 from tests import helpers as H
 
 FAST_CASES = [n for n in H.golden_names()
-              if n.split("_")[0] in ("d16", "d32", "m24", "n24", "cg32", "cgm24", "m32", "nb24", "nbg24", "nbgd32", "nc24", "o1m24", "o1cgm24", "chm24", "chd32", "q24", "qd40", "qcg40", "l48") or n in ("d64_111", "d64_cheb_111", "d64_118", "d64_cheb_118")]
+              if n.split("_")[0] in ("d16", "d32", "m24", "n24", "cg32", "cgm24", "m32", "nb24", "nbg24", "nbgd32", "nc24", "e25", "tiny6", "o1m24", "o1cgm24", "chm24", "chd32", "q24", "qd40", "qcg40", "l48") or n in ("d64_111", "d64_cheb_111", "d64_118", "d64_cheb_118")]
 SLOW_CASES = [n for n in H.golden_names() if n not in FAST_CASES]
 
 
